@@ -1,0 +1,206 @@
+#!/usr/bin/env python
+"""Generates the golden vectors under tests/golden/ from the UNMODIFIED reference
+(oracle/_ref/libpcd_ref.so = /root/reference/src/*.cpp behind oracle/ref_harness.cpp).
+
+Runs only in the build container (needs /root/reference); the .npz files it writes are
+committed, this script is their provenance.
+
+    python tests/golden/make_golden.py images            # inputs: RGB bytes of the 3 reference images
+    python tests/golden/make_golden.py full c1|c2|c3      # end-to-end runs (main.cpp:216-262), threads=1
+    python tests/golden/make_golden.py stages             # per-stage dumps on small meshes
+    python tests/golden/make_golden.py solver             # poisson_solver known-answer cases
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+# BASELINE.json configs[0..2]; lens parameters as SURVEY App. B (CLI floats: 0.1f, 0.01f ...)
+FULL = {
+    "c1": dict(image="siggraph", res_w=100, mesh_width=0.5, focal_l=1.5, thickness=0.1, conv_tres=0.01),
+    "c2": dict(image="lena", res_w=256, mesh_width=0.5, focal_l=1.5, thickness=0.1, conv_tres=0.01),
+    "c3": dict(image="hello", res_w=256, mesh_width=0.5, focal_l=1.5, thickness=0.1, conv_tres=0.01),
+}
+
+
+def synth_image(w: int, h: int, seed: int) -> np.ndarray:
+    """Small smooth-plus-edges test density in [0,1] (8-bit quantised like a PNG would be)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    img = np.full((h, w), 0.05)
+    for _ in range(3):
+        cx, cy = rng.uniform(0.2, 0.8) * w, rng.uniform(0.2, 0.8) * h
+        s = rng.uniform(0.08, 0.2) * w
+        img += rng.uniform(0.4, 1.0) * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
+    cx, cy, r = rng.uniform(0.3, 0.7) * w, rng.uniform(0.3, 0.7) * h, 0.15 * min(w, h)
+    img[(xx - cx) ** 2 + (yy - cy) ** 2 < r * r] = 1.0
+    img = np.clip(img, 0, 1)
+    return np.round(img * 255.0) / 255.0
+
+
+def load_rgb(name: str) -> np.ndarray:
+    return np.load(os.path.join(GOLD, "images.npz"))[name]
+
+
+def gray_of(rgb: np.ndarray) -> np.ndarray:
+    return O.rgba_to_gray(rgb)
+
+
+def cmd_images():
+    from PIL import Image
+    out = {}
+    for name in ("siggraph", "lena", "hello"):
+        rgba = np.asarray(Image.open(f"{O.REFERENCE_ROOT}/img/{name}.png").convert("RGBA"))
+        out[name] = np.ascontiguousarray(rgba[..., :3])
+        print(name, rgba.shape)
+    np.savez_compressed(os.path.join(GOLD, "images.npz"), **out)
+
+
+def cmd_full(key: str):
+    cfg = FULL[key]
+    ref = O.RefLib()
+    gray = gray_of(load_rgb(cfg["image"]))
+    s, img = O.prepare_image(gray, cfg["res_w"], O.f32(cfg["mesh_width"]), O.f32(cfg["focal_l"]),
+                             O.f32(cfg["thickness"]))
+    conv = O.f32(cfg["conv_tres"])
+    d = ref.design(s, threads=1)
+    t0 = time.time()
+    d.initialize_solvers(img)
+    out = {"target_areas": d.get("target_areas")}
+    steps = []
+    snaps = {}
+    for itr in range(50):                                   # main.cpp:243-256
+        step = d.transport_iteration()
+        steps.append(step)
+        print(f"[{key}] iter {itr} step {step:.9f}  ({time.time() - t0:.0f}s)", flush=True)
+        if itr in (0, 5):                                   # pre-fold snapshots
+            snaps[f"target_x_it{itr}"] = d.get("target_x")
+            snaps[f"target_y_it{itr}"] = d.get("target_y")
+        if step < conv:
+            break
+    out["steps"] = np.array(steps)
+    out.update(snaps)
+    out["target_x"], out["target_y"] = d.get("target_x"), d.get("target_y")
+    ivx, ivy = d.inverted_transport_map()
+    out["inverted_x"], out["inverted_y"] = ivx, ivy
+    zs = []
+    for itr in range(3):                                    # main.cpp:260-262
+        d.height_iteration(itr)
+        zs.append(d.get("source_z"))
+    out["source_z_it0"], out["source_z_it1"], out["source_z"] = zs
+    h = d.get("h")
+    out["h_range"] = np.array([h.min(), h.max()])
+    out["h_sub8"] = np.ascontiguousarray(h[::8, ::8])
+    if key == "c1":
+        out["h"] = h
+    obj = os.path.join(GOLD, f"_{key}_output.obj")
+    d.save_obj(obj)
+    with open(obj, "rb") as f:
+        data = f.read()
+    import hashlib
+    out["obj_md5"] = np.frombuffer(hashlib.md5(data).hexdigest().encode(), dtype=np.uint8)
+    lines = data.decode().split("\n")
+    out["obj_head"] = np.frombuffer("\n".join(lines[:12]).encode(), dtype=np.uint8)
+    out["obj_nlines"] = np.array([len(lines)])
+    os.remove(obj)
+    out["params"] = np.array([s.mesh_nx, s.mesh_ny, s.res_x, s.res_y, s.width, s.height, s.focal_l,
+                              s.thickness, conv])
+    out["wall_s"] = np.array([time.time() - t0])
+    np.savez_compressed(os.path.join(GOLD, f"full_{key}.npz"), **out)
+    print(f"[{key}] done: {len(steps)} iterations, {time.time() - t0:.0f}s")
+
+
+STAGE_CASES = {
+    # name: (img_w, img_h, res_w, seed, n_transport_iters)
+    "sq16": (64, 64, 16, 1, 3),
+    "sq33": (132, 132, 33, 2, 2),
+    "rect32x16": (128, 64, 32, 3, 3),
+    "rect24x8": (96, 32, 24, 4, 2),
+}
+
+
+def cmd_stages():
+    ref = O.RefLib()
+    for name, (iw, ih, res_w, seed, n_it) in STAGE_CASES.items():
+        gray = synth_image(iw, ih, seed)
+        s, img = O.prepare_image(gray, res_w, O.f32(0.5), O.f32(1.5), O.f32(0.1))
+        d = ref.design(s, threads=1)
+        d.initialize_solvers(img)
+        out = {"image": img,
+               "params": np.array([s.mesh_nx, s.mesh_ny, s.res_x, s.res_y, s.width, s.height, s.focal_l,
+                                   s.thickness]),
+               "pixels": d.get("pixels"), "target_areas": d.get("target_areas")}
+        for it in range(n_it):
+            pre = {f"it{it}_pre_target_x": d.get("target_x"), f"it{it}_pre_target_y": d.get("target_y"),
+                   f"it{it}_pre_phi": d.get("phi")}
+            step = d.transport_iteration()
+            out.update(pre)
+            out[f"it{it}_step"] = np.array([step])
+            for f in ("errors", "raster", "phi", "gradient_x", "gradient_y", "vertex_gradient_x",
+                      "vertex_gradient_y", "target_x", "target_y"):
+                out[f"it{it}_{f}"] = d.get(f)
+        ivx, ivy = d.inverted_transport_map()
+        out["inverted_x"], out["inverted_y"] = ivx, ivy
+        for it in range(3):
+            out[f"h{it}_pre_h"] = d.get("h")
+            out[f"h{it}_pre_source_z"] = d.get("source_z")
+            d.height_iteration(it)
+            for f in ("normals_x", "normals_y", "norm_x", "norm_y", "divergence", "h", "source_z"):
+                out[f"h{it}_{f}"] = d.get(f)
+        d.close()
+        np.savez_compressed(os.path.join(GOLD, f"stages_{name}.npz"), **out)
+        print("stages", name, "ok")
+
+
+def cmd_solver():
+    """poisson_solver (src/solver.cpp:70-147) known-answer cases, threads=1."""
+    ref = O.RefLib()
+    rng = np.random.RandomState(7)
+    out = {}
+    cases = {"sq48": (48, 48), "rect64x24": (64, 24), "rect20x50": (20, 50), "tiny3x2": (3, 2), "row1x9": (9, 1)}
+    for name, (w, h) in cases.items():
+        D = rng.standard_normal((h, w))
+        D -= D.mean()
+        phi0 = np.zeros((h, w))
+        out[f"{name}_D"] = D
+        for k in (1, 2, 7):
+            out[f"{name}_phi_k{k}"] = ref.poisson_solver(D, phi0, k, 0.0)
+        out[f"{name}_phi_conv"] = ref.poisson_solver(D, phi0, 100000, 1e-7)
+        # warm start: continue from the converged field with a tighter tolerance
+        out[f"{name}_phi_warm"] = ref.poisson_solver(D, out[f"{name}_phi_conv"], 100000, 1e-9)
+    # NaN holes (src/solver.cpp:29-44): a masked block and a masked border cell
+    w, h = 40, 30
+    D = rng.standard_normal((h, w))
+    D[10:14, 12:20] = np.nan
+    D[0, 5] = np.nan
+    D[np.isfinite(D)] -= D[np.isfinite(D)].mean()
+    out["nan_D"] = D
+    out["nan_phi_k5"] = ref.poisson_solver(D, np.zeros((h, w)), 5, 0.0)
+    out["nan_phi_k200"] = ref.poisson_solver(D, np.zeros((h, w)), 200, 0.0)
+    # max_iterations cap binding
+    out["cap_phi"] = ref.poisson_solver(out["sq48_D"], np.zeros((48, 48)), 13, 1e-30)
+    np.savez_compressed(os.path.join(GOLD, "solver.npz"), **out)
+    print("solver ok")
+
+
+if __name__ == "__main__":
+    cmd = sys.argv[1]
+    if cmd == "images":
+        cmd_images()
+    elif cmd == "full":
+        cmd_full(sys.argv[2])
+    elif cmd == "stages":
+        cmd_stages()
+    elif cmd == "solver":
+        cmd_solver()
+    else:
+        raise SystemExit(__doc__)
