@@ -1,0 +1,143 @@
+/* pcd.h -- C ABI of the B200-native caustic-design hot path (libpcd_b200.so).
+ *
+ * The reference (dylanmsu/poisson_caustic_design) has no FFI: its boundary is the C++ API
+ *   void poisson_solver(vector<vector<double>>& D, vector<vector<double>>& phi, int width, int height,
+ *                       int max_iterations, double convergence_threshold, int max_threads)   src/solver.h:8
+ *   class Caustic_design { ... }                                                             src/caustic_design.h:7-66
+ * and the CLI in main.cpp:137-272.  The host C++ shim under poisson_caustic_design_b200/host/ keeps those
+ * signatures and calls only the functions below.  Everything here is plain pointers and sizes; all
+ * arithmetic is fp64; grids are flat row-major [y*W + x]; points are SoA.
+ *
+ * Conventions: every call returns a pcd_status (0 = ok); no exceptions and no stdout cross this
+ * boundary; pcd_last_error() gives the message of the last failure on the calling thread.  A
+ * context / solver is not thread-safe; distinct ones are independent.  All pointers are HOST pointers
+ * unless the name says `_dev`.
+ */
+#ifndef PCD_H
+#define PCD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCD_ABI_VERSION 1
+
+typedef enum pcd_status {
+    PCD_OK = 0,
+    PCD_ERR_INVALID = 1,      /* bad argument / size */
+    PCD_ERR_CUDA = 2,         /* a CUDA runtime call failed (message has the CUDA error string) */
+    PCD_ERR_NO_DEVICE = 3,    /* no usable CUDA device: the library never falls back to a CPU path */
+    PCD_ERR_RASTER_MISS = 4,  /* a raster / inverse-map sample hit no triangle; the reference exit(0)s here, src/mesh.cpp:276-281 */
+    PCD_ERR_STATE = 5,        /* call order (e.g. iteration before pcd_initialize_solvers) */
+    PCD_ERR_UNSUPPORTED = 6
+} pcd_status;
+
+/* Public data members of Caustic_design / Mesh (src/caustic_design.h:16-30, src/mesh.h:51-52), flattened.
+ * Grid fields have res_x*res_y elements, vertex fields mesh_res_x*mesh_res_y. */
+typedef enum pcd_field {
+    PCD_FIELD_PHI = 0,              /* grid  */
+    PCD_FIELD_H = 1,                /* grid  */
+    PCD_FIELD_RASTER = 2,           /* grid, mean-removed D as handed to the solver */
+    PCD_FIELD_PIXELS = 3,           /* grid  */
+    PCD_FIELD_DIVERGENCE = 4,       /* grid, mean-removed */
+    PCD_FIELD_NORM_X = 5,           /* grid  */
+    PCD_FIELD_NORM_Y = 6,           /* grid  */
+    PCD_FIELD_GRADIENT_X = 7,       /* grid, computed on demand from phi (never materialised on the hot path) */
+    PCD_FIELD_GRADIENT_Y = 8,       /* grid, on demand */
+    PCD_FIELD_ERRORS = 9,           /* vertex */
+    PCD_FIELD_TARGET_AREAS = 10,    /* vertex */
+    PCD_FIELD_VERTEX_GRADIENT_X = 11,
+    PCD_FIELD_VERTEX_GRADIENT_Y = 12,
+    PCD_FIELD_NORMALS_X = 13,
+    PCD_FIELD_NORMALS_Y = 14,
+    PCD_FIELD_TARGET_X = 15,        /* mesh->target_points[i][0] */
+    PCD_FIELD_TARGET_Y = 16,
+    PCD_FIELD_TARGET_Z = 17,
+    PCD_FIELD_SOURCE_X = 18,        /* mesh->source_points[i][0] */
+    PCD_FIELD_SOURCE_Y = 19,
+    PCD_FIELD_SOURCE_Z = 20,
+    PCD_FIELD_COUNT = 21
+} pcd_field;
+
+/* Which SOR kernel family runs a solve. */
+typedef enum pcd_solver_path {
+    PCD_SOLVER_AUTO = 0,       /* resident when the grid fits on chip, streaming otherwise */
+    PCD_SOLVER_STREAMING = 1,  /* one launch per colour, phi/D streamed from HBM/L2 */
+    PCD_SOLVER_RESIDENT = 2    /* one persistent cooperative kernel, phi/D tiles live in shared memory */
+} pcd_solver_path;
+
+typedef struct pcd_config {
+    int mesh_res_x, mesh_res_y;   /* Caustic_design::set_mesh_resolution    src/caustic_design.cpp:28-31 */
+    int res_x, res_y;             /* Caustic_design::set_domain_resolution  :33-36 */
+    double width, height;         /* Caustic_design::set_mesh_size          :38-41 */
+    double focal_l;               /* set_lens_focal_length                  :43-45 */
+    double thickness;             /* set_lens_thickness                     :47-49 */
+    int device;                   /* CUDA device ordinal */
+    int solver_path;              /* pcd_solver_path */
+} pcd_config;
+
+typedef struct pcd_solve_info {
+    int sweeps;             /* full red+black sweeps executed */
+    int converged_at;       /* sweeps up to and including the first with max|delta| < tol; 0 = cap hit */
+    double last_max_update; /* max|delta| of the sweep that satisfied the test (or of the last sweep) */
+    double device_ms;       /* CUDA-event time of the solve on its stream */
+    int launches;           /* kernel launches issued by the solve */
+    int path;               /* pcd_solver_path actually used */
+} pcd_solve_info;
+
+typedef struct pcd_ctx pcd_ctx;
+typedef struct pcd_solver pcd_solver;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int pcd_abi_version(void);
+const char *pcd_last_error(void);
+int pcd_device_count(int *count);
+/* total kernel launches issued by this library in this process (bench.py's gpu_launches) */
+long long pcd_launch_count(void);
+
+/* ---- class Caustic_design (src/caustic_design.h:7-66) ---------------------------------------- */
+int pcd_create(const pcd_config *cfg, pcd_ctx **out);                     /* ctor + setters :5-53 */
+void pcd_destroy(pcd_ctx *ctx);
+int pcd_initialize_solvers(pcd_ctx *ctx, const double *image);            /* :334-364  image[res_y*res_x] */
+int pcd_perform_transport_iteration(pcd_ctx *ctx, double *step_out);      /* :190-266 */
+int pcd_perform_height_map_iteration(pcd_ctx *ctx, int itr, double *update_sum_out /* may be NULL */); /* :269-332 */
+/* Runs main.cpp:243-256 on the device (<= max_iters iterations, stop when step < conv_tres) with a
+ * single host read of the step per iteration; steps_out (may be NULL) receives each step. */
+int pcd_run_transport(pcd_ctx *ctx, int max_iters, double conv_tres, int *iters_out, double *steps_out);
+int pcd_field_size(const pcd_ctx *ctx, int field, long *n_out);
+int pcd_get_field(pcd_ctx *ctx, int field, double *dst);
+int pcd_set_field(pcd_ctx *ctx, int field, const double *src);            /* members are public in the reference */
+int pcd_inverted_transport_map(pcd_ctx *ctx, double *out_x, double *out_y); /* Mesh::calculate_inverted_transport_map src/mesh.cpp:348-409 */
+int pcd_last_solve_info(const pcd_ctx *ctx, pcd_solve_info *info);
+/* stage entry points (per-stage parity tests drive these with the oracle's inputs) */
+int pcd_stage_errors(pcd_ctx *ctx);                                       /* caustic_design.cpp:194-209 */
+int pcd_stage_raster(pcd_ctx *ctx);                                       /* :212-213, no mean removal */
+int pcd_stage_subtract_average(pcd_ctx *ctx);                             /* :221 */
+int pcd_stage_solve_transport(pcd_ctx *ctx);                              /* :222 */
+int pcd_stage_step(pcd_ctx *ctx, double *step_out);                       /* :225-265 */
+
+/* ---- poisson_solver (src/solver.h:8) ----------------------------------------------------------- */
+/* One-shot drop-in: D and phi are host arrays [height*width]; phi is in/out (warm start).  max_threads of
+ * the reference has no meaning here. */
+int pcd_poisson_solver(const double *D, double *phi, int width, int height, int max_iterations,
+                       double convergence_threshold, int device, pcd_solve_info *info /* may be NULL */);
+
+/* Device-resident solver object (bench / repeated solves / explicit path selection). */
+int pcd_solver_create(int width, int height, int device, int solver_path, pcd_solver **out);
+void pcd_solver_destroy(pcd_solver *s);
+int pcd_solver_upload(pcd_solver *s, const double *D /* or NULL */, const double *phi /* or NULL */);
+int pcd_solver_download(pcd_solver *s, double *phi);
+/* check_lag: convergence of sweep s is acted on after sweep s+check_lag (resident path) or at the next
+ * multiple of check_lag (streaming path); <= 0 selects the default.  The field is bit-identical to
+ * the red-black oracle run for `sweeps` sweeps. */
+int pcd_solver_set_check_lag(pcd_solver *s, int check_lag);
+int pcd_solver_run(pcd_solver *s, int max_iterations, double convergence_threshold, pcd_solve_info *info);
+int pcd_solver_path_used(const pcd_solver *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCD_H */

@@ -1,0 +1,132 @@
+// Internal declarations shared by the .cu translation units of libpcd_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "pcd.h"
+
+namespace pcd {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define PCD_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            ::pcd::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                             __LINE__);                                                         \
+            return PCD_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define PCD_TRY(expr)                \
+    do {                             \
+        int _s = (expr);             \
+        if (_s != PCD_OK) return _s; \
+    } while (0)
+
+// counts the launch and checks the launch error
+#define PCD_LAUNCHED()                                                                      \
+    do {                                                                                    \
+        ::pcd::g_launches.fetch_add(1, std::memory_order_relaxed);                          \
+        cudaError_t _e = cudaGetLastError();                                                \
+        if (_e != cudaSuccess) {                                                            \
+            ::pcd::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),    \
+                             __FILE__, __LINE__);                                           \
+            return PCD_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+int select_device(int device);
+
+// ---- solver -----------------------------------------------------------------------------------
+// omega = 2/(1+pi/W) with the reference's truncated pi, src/solver.cpp:71
+inline double sor_omega(int W) { return 2.0 / (1.0 + 3.14159265 / W); }
+
+}  // namespace pcd
+
+struct pcd_solver {
+    int W = 0, H = 0, device = 0;
+    int path_req = PCD_SOLVER_AUTO, path_used = PCD_SOLVER_STREAMING;
+    int check_lag = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    double *D = nullptr, *phi = nullptr;  // owned device arrays (standalone use)
+    bool own_fields = false;
+    unsigned long long *sweep_max = nullptr;  // device: per-sweep max|delta| bit patterns (ring)
+    unsigned long long *h_sweep_max = nullptr;  // pinned host mirror
+    int ring = 0;
+    unsigned char *mask = nullptr;  // device: 4-bit neighbour masks, only when D has NaN holes
+    int *d_flags = nullptr;         // device scratch: [0] = D has NaN
+    int *h_flags = nullptr;         // pinned
+    // resident path
+    void *res_state = nullptr;      // device: control block of the persistent kernel
+    void *h_res_state = nullptr;    // pinned mirror
+    double *halo = nullptr;         // device: boundary-row exchange buffers
+    int res_ctas = 0, res_threads = 0, res_rows_per_cta = 0;
+    size_t res_smem = 0;
+    int sm_count = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace pcd {
+int solver_init(pcd_solver *s, int W, int H, int device, int path, cudaStream_t stream);
+void solver_free(pcd_solver *s);
+// D_dev / phi_dev: device arrays of W*H doubles; phi in/out
+int solver_run(pcd_solver *s, const double *D_dev, double *phi_dev, int max_iterations, double tol,
+               pcd_solve_info *info);
+}  // namespace pcd
+
+struct pcd_ctx {
+    pcd_config cfg{};
+    int V = 0, T = 0;
+    long N = 0;
+    cudaStream_t stream = nullptr;
+    bool initialized = false;
+    // mesh (SoA)
+    double *tx = nullptr, *ty = nullptr, *tz = nullptr, *sx = nullptr, *sy = nullptr, *sz = nullptr;
+    // fields
+    double *pixels = nullptr, *target_areas = nullptr, *errors = nullptr, *raster = nullptr, *phi = nullptr,
+           *h = nullptr, *vgx = nullptr, *vgy = nullptr, *normals_x = nullptr, *normals_y = nullptr,
+           *norm_x = nullptr, *norm_y = nullptr, *divergence = nullptr, *inv_x = nullptr, *inv_y = nullptr,
+           *hv = nullptr;
+    // sample lattices: domain nodes (src/mesh.cpp:241-253) and inverse-map queries (:356-360)
+    double *xs = nullptr, *ys = nullptr, *qxs = nullptr, *qys = nullptr;
+    int *owner = nullptr;      // N: owning triangle of each domain sample in the deformed (target) mesh
+    int *owner_src = nullptr;  // N: same for the regular (source) mesh, computed once
+    bool owner_src_valid = false;
+    int *owner_v = nullptr;    // V: owning triangle of each inverse-map query
+    // reductions
+    double *partials = nullptr;  // device scratch for deterministic two-stage sums
+    int n_partials = 0;
+    double *d_scalars = nullptr;  // device: small result slots
+    double *h_scalars = nullptr;  // pinned mirror
+    unsigned long long *d_bits = nullptr;  // device: atomicMax/Min slots
+    int *d_flags = nullptr, *h_flags = nullptr;
+    pcd_solver solver;
+    pcd_solve_info last{};
+};
+
+namespace pcd {
+// init_kernels.cu
+int k_init(pcd_ctx *c, const double *image_host);
+// transport_kernels.cu
+int k_errors(pcd_ctx *c);
+int k_raster_target(pcd_ctx *c);            // errors -> raster (nodal samples of the deformed mesh)
+int k_subtract_average(pcd_ctx *c, double *grid);
+int k_step(pcd_ctx *c, double *step_out_host);  // gradient+bilinear+step_grid+max displacement
+int k_gradient(pcd_ctx *c, const double *grid, double *gx, double *gy);
+// height_kernels.cu
+int k_inverse_map(pcd_ctx *c);              // -> inv_x, inv_y
+int k_height_iteration(pcd_ctx *c, double *update_sum_host);
+// shared helpers
+int check_miss(pcd_ctx *c, const char *what);
+}  // namespace pcd

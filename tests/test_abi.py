@@ -1,0 +1,46 @@
+"""CPU: the C-ABI library loads and exports every symbol include/pcd.h declares; without a GPU the
+product path fails loudly (no CPU fallback); the product never imports the oracle."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "pcd.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcd_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(pcd):
+    L = ctypes.CDLL(pcd.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/pcd.h but not exported"
+    assert sorted(n for n, _, _ in pcd.ABI) == syms, "python binding table out of sync with include/pcd.h"
+    assert pcd.lib().pcd_abi_version() == 1
+
+
+def test_no_cpu_fallback(pcd):
+    if pcd.device_count() > 0:
+        pytest.skip("a GPU is present")
+    import numpy as np
+    with pytest.raises(pcd.PcdError) as e:
+        pcd.poisson_solver(np.zeros((4, 4)), np.zeros((4, 4)), 4, 4, 10, 1e-7)
+    assert e.value.status == pcd.PCD_ERR_NO_DEVICE
+    with pytest.raises(pcd.PcdError):
+        pcd.Solver(8, 8)
+
+
+def test_product_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "poisson_caustic_design_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                for needle in ("pcd_oracle.h", "libpcd_oracle", "libpcd_ref", "pcdo_", "import oracle", "from oracle"):
+                    assert needle not in src, f"{f} references the oracle ({needle})"

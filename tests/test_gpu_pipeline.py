@@ -1,0 +1,78 @@
+"""GPU: the whole path (init -> transport loop -> 3 height iterations) through the C ABI against the
+reference's own end-to-end runs (tests/golden/full_c*.npz from oracle/_ref, threads=1).
+
+Tolerances (BASELINE.json north_star): equal transport-iteration count (+-1), final vertex
+displacement rel L-inf <= 1e-3 of the max displacement (rasteriser tie-break under mesh folds), heights rel
+L-inf <= 1e-4 of their range, pre-fold iterations <= 1e-6."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = {
+    "c1": ("siggraph", 100),   # BASELINE.json configs[0]
+    "c2": ("lena", 256),       # configs[1]
+    "c3": ("hello", 256),      # configs[2], non-square
+}
+
+
+@pytest.mark.parametrize("key", ["c1", "c2", "c3"])
+def test_end_to_end_matches_reference(pcd, oracle_mod, golden, key):
+    path = os.path.join(GOLD, f"full_{key}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated yet")
+    g = golden(f"full_{key}")
+    image, res_w = CONFIGS[key]
+    O = oracle_mod
+    gray = O.rgba_to_gray(golden("images")[image])
+    s, resized = O.prepare_image(gray, res_w, O.f32(0.5), O.f32(1.5), O.f32(0.1))
+    conv = O.f32(0.01)
+    cd = pcd.from_setup(s)
+    cd.initialize_solvers(resized)
+    sub = int(g["vertex_sub"][0])          # big fixtures keep every sub-th vertex in x and y
+
+    def vget(name):
+        return np.ascontiguousarray(cd.get(name).reshape(s.mesh_ny, s.mesh_nx)[::sub, ::sub]).ravel()
+
+    def vsub(a):
+        return np.ascontiguousarray(np.asarray(a).reshape(s.mesh_ny, s.mesh_nx)[::sub, ::sub]).ravel()
+
+    assert np.abs(vget("target_areas") - g["target_areas"]).max() < 1e-12 * g["target_areas"].max()
+    assert abs(cd.get("target_areas").sum() - g["target_areas_sum"][0]) < 1e-12
+    sx0, sy0 = vget("source_x"), vget("source_y")
+    steps = []
+    for itr in range(50):
+        step = cd.perform_transport_iteration()
+        steps.append(step)
+        if itr in (0, 5) and f"target_x_it{itr}" in g:
+            d = max(np.abs(vget("target_x") - g[f"target_x_it{itr}"]).max(),
+                    np.abs(vget("target_y") - g[f"target_y_it{itr}"]).max())
+            disp = max(np.abs(g[f"target_x_it{itr}"] - sx0).max(), np.abs(g[f"target_y_it{itr}"] - sy0).max())
+            assert d <= 1e-6 * disp, (key, itr, d, disp)
+        if step < conv:
+            break
+    ref_steps = g["steps"]
+    assert abs(len(steps) - len(ref_steps)) <= 1, (steps, ref_steps)
+    n = min(len(steps), len(ref_steps))
+    assert np.abs(np.array(steps[:n]) - ref_steps[:n]).max() < 1e-5
+    if len(steps) == len(ref_steps):
+        tx, ty = vget("target_x"), vget("target_y")
+        disp = max(np.abs(g["target_x"] - sx0).max(), np.abs(g["target_y"] - sy0).max())
+        d = max(np.abs(tx - g["target_x"]).max(), np.abs(ty - g["target_y"]).max())
+        assert d <= 1e-3 * disp, (key, d, disp)
+        ix, iy = cd.inverted_transport_map()
+        assert max(np.abs(vsub(ix) - g["inverted_x"]).max(), np.abs(vsub(iy) - g["inverted_y"]).max()) <= 5e-3 * s.width
+    for hi in range(3):
+        cd.perform_height_map_iteration(hi)
+    if len(steps) == len(ref_steps):
+        z, zr = vget("source_z"), g["source_z"]
+        rng = zr.max() - zr.min()
+        assert np.abs(z - zr).max() <= 1e-4 * rng, (key, np.abs(z - zr).max(), rng)
+        h = cd.get("h")
+        hs, hr = h[::8, ::8], g["h_sub8"]
+        assert np.abs((hs - hs.mean()) - (hr - hr.mean())).max() <= 2e-4 * (g["h_range"][1] - g["h_range"][0])
+    cd.close()
