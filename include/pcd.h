@@ -83,7 +83,8 @@ typedef struct pcd_solve_info {
     int sweeps;             /* full red+black sweeps executed */
     int converged_at;       /* sweeps up to and including the first with max|delta| < tol; 0 = cap hit */
     double last_max_update; /* max|delta| of the sweep that satisfied the test (or of the last sweep) */
-    double device_ms;       /* CUDA-event time of the solve on its stream */
+    double device_ms;       /* CUDA-event time of the whole solve on its stream */
+    double kernel_ms;       /* CUDA-event time of the SOR kernel launches alone (roofline numerator's clock) */
     int launches;           /* kernel launches issued by the solve */
     int path;               /* pcd_solver_path actually used */
 } pcd_solve_info;
@@ -112,6 +113,13 @@ int pcd_get_field(pcd_ctx *ctx, int field, double *dst);
 int pcd_set_field(pcd_ctx *ctx, int field, const double *src);            /* members are public in the reference */
 int pcd_inverted_transport_map(pcd_ctx *ctx, double *out_x, double *out_y); /* Mesh::calculate_inverted_transport_map src/mesh.cpp:348-409 */
 int pcd_last_solve_info(const pcd_ctx *ctx, pcd_solve_info *info);
+/* totals over every solve since the last reset: sweeps, launches, kernel_ms, device_ms are summed */
+int pcd_solve_totals(pcd_ctx *ctx, pcd_solve_info *totals, int reset);
+/* device timing on the context's own stream (torch.cuda.Event only sees torch's stream): slots 0..7 */
+int pcd_event_record(pcd_ctx *ctx, int slot);
+int pcd_event_elapsed_ms(pcd_ctx *ctx, int slot_start, int slot_stop, double *ms_out);
+/* evicts L2 by writing a 256 MiB scratch buffer on the context's stream (bench hygiene between steps) */
+int pcd_flush_l2(pcd_ctx *ctx);
 /* stage entry points (per-stage parity tests drive these with the oracle's inputs) */
 int pcd_stage_errors(pcd_ctx *ctx);                                       /* caustic_design.cpp:194-209 */
 int pcd_stage_raster(pcd_ctx *ctx);                                       /* :212-213, no mean removal */

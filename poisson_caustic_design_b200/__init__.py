@@ -46,11 +46,11 @@ class pcd_config(C.Structure):
 
 class pcd_solve_info(C.Structure):
     _fields_ = [("sweeps", C.c_int), ("converged_at", C.c_int), ("last_max_update", C.c_double),
-                ("device_ms", C.c_double), ("launches", C.c_int), ("path", C.c_int)]
+                ("device_ms", C.c_double), ("kernel_ms", C.c_double), ("launches", C.c_int), ("path", C.c_int)]
 
     def as_dict(self):
         return {"sweeps": self.sweeps, "converged_at": self.converged_at, "last_max_update": self.last_max_update,
-                "device_ms": self.device_ms, "launches": self.launches, "path": SOLVER_PATH_NAMES.get(self.path, "?")}
+                "device_ms": self.device_ms, "kernel_ms": self.kernel_ms, "launches": self.launches, "path": SOLVER_PATH_NAMES.get(self.path, "?")}
 
 
 _dp = C.POINTER(C.c_double)
@@ -73,6 +73,10 @@ ABI = [
     ("pcd_set_field", C.c_int, [C.c_void_p, C.c_int, _dp]),
     ("pcd_inverted_transport_map", C.c_int, [C.c_void_p, _dp, _dp]),
     ("pcd_last_solve_info", C.c_int, [C.c_void_p, C.POINTER(pcd_solve_info)]),
+    ("pcd_solve_totals", C.c_int, [C.c_void_p, C.POINTER(pcd_solve_info), C.c_int]),
+    ("pcd_event_record", C.c_int, [C.c_void_p, C.c_int]),
+    ("pcd_event_elapsed_ms", C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp]),
+    ("pcd_flush_l2", C.c_int, [C.c_void_p]),
     ("pcd_stage_errors", C.c_int, [C.c_void_p]),
     ("pcd_stage_raster", C.c_int, [C.c_void_p]),
     ("pcd_stage_subtract_average", C.c_int, [C.c_void_p]),
@@ -241,6 +245,30 @@ class CausticDesign:
         info = pcd_solve_info()
         _check(lib().pcd_last_solve_info(self._h, C.byref(info)))
         return info.as_dict()
+
+    def solve_totals(self, reset: bool = False) -> dict:
+        info = pcd_solve_info()
+        _check(lib().pcd_solve_totals(self._h, C.byref(info), int(reset)))
+        return info.as_dict()
+
+    def event_record(self, slot: int):
+        _check(lib().pcd_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, start: int, stop: int) -> float:
+        ms = C.c_double(0.0)
+        _check(lib().pcd_event_elapsed_ms(self._h, start, stop, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        _check(lib().pcd_flush_l2(self._h))
+
+    def get_into(self, name: str, out: np.ndarray):
+        """Device -> caller-provided (e.g. pinned) host buffer."""
+        _check(lib().pcd_get_field(self._h, FIELDS[name], _p(out)))
+
+    def set_from(self, name: str, src: np.ndarray):
+        """Caller-provided (e.g. pinned) host buffer -> device."""
+        _check(lib().pcd_set_field(self._h, FIELDS[name], _p(src)))
 
     def get(self, name: str) -> np.ndarray:
         n = C.c_long(0)

@@ -77,6 +77,8 @@ static void ctx_free(pcd_ctx *c) {
     cudaFree(c->owner); cudaFree(c->owner_src); cudaFree(c->owner_v); cudaFree(c->d_bits); cudaFree(c->d_flags);
     cudaFreeHost(c->h_scalars); cudaFreeHost(c->h_flags);
     solver_free(&c->solver);
+    for (cudaEvent_t e : c->events) if (e) cudaEventDestroy(e);
+    cudaFree(c->l2_scratch);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -103,7 +105,10 @@ static int ctx_alloc(pcd_ctx *c) {
     PCD_TRY(dmalloc(&c->d_flags, 4));
     PCD_CUDA(cudaMallocHost(&c->h_scalars, sizeof(double) * 8));
     PCD_CUDA(cudaMallocHost(&c->h_flags, sizeof(int) * 4));
+    for (cudaEvent_t &e : c->events) PCD_CUDA(cudaEventCreate(&e));
     PCD_TRY(solver_init(&c->solver, c->cfg.res_x, c->cfg.res_y, c->cfg.device, c->cfg.solver_path, c->stream));
+    // the zero-fills above ran on the legacy default stream, which non-blocking streams do not wait for
+    PCD_CUDA(cudaDeviceSynchronize());
     return PCD_OK;
 }
 
@@ -184,7 +189,7 @@ int pcd_stage_raster(pcd_ctx *ctx) {
 int pcd_stage_subtract_average(pcd_ctx *ctx) { NEED_INIT(ctx); return k_subtract_average(ctx, ctx->raster); }
 int pcd_stage_solve_transport(pcd_ctx *ctx) {
     NEED_INIT(ctx);
-    return solver_run(&ctx->solver, ctx->raster, ctx->phi, 100000, 0.0000001, &ctx->last);  // caustic_design.cpp:222
+    return ctx_solve(ctx, ctx->raster, ctx->phi, 0.0000001);  // caustic_design.cpp:222
 }
 int pcd_stage_step(pcd_ctx *ctx, double *step_out) {
     NEED_INIT(ctx);
@@ -200,7 +205,7 @@ int pcd_perform_transport_iteration(pcd_ctx *ctx, double *step_out) {
     PCD_TRY(k_raster_target(ctx));
     PCD_TRY(check_miss(ctx, "target raster"));
     PCD_TRY(k_subtract_average(ctx, ctx->raster));
-    PCD_TRY(solver_run(&ctx->solver, ctx->raster, ctx->phi, 100000, 0.0000001, &ctx->last));
+    PCD_TRY(ctx_solve(ctx, ctx->raster, ctx->phi, 0.0000001));
     double s = 0.0;
     PCD_TRY(k_step(ctx, &s));
     if (step_out) *step_out = s;
@@ -290,6 +295,38 @@ int pcd_last_solve_info(const pcd_ctx *ctx, pcd_solve_info *info) {
     return PCD_OK;
 }
 
+int pcd_solve_totals(pcd_ctx *ctx, pcd_solve_info *totals, int reset) {
+    if (!ctx) { set_error("null argument"); return PCD_ERR_INVALID; }
+    if (totals) *totals = ctx->totals;
+    if (reset) ctx->totals = pcd_solve_info{};
+    return PCD_OK;
+}
+
+int pcd_event_record(pcd_ctx *ctx, int slot) {
+    NEED_CTX(ctx);
+    if (slot < 0 || slot >= 8) { set_error("event slot %d out of range", slot); return PCD_ERR_INVALID; }
+    PCD_CUDA(cudaEventRecord(ctx->events[slot], ctx->stream));
+    return PCD_OK;
+}
+
+int pcd_event_elapsed_ms(pcd_ctx *ctx, int slot_start, int slot_stop, double *ms_out) {
+    NEED_CTX(ctx);
+    if (slot_start < 0 || slot_start >= 8 || slot_stop < 0 || slot_stop >= 8 || !ms_out) { set_error("bad event slots"); return PCD_ERR_INVALID; }
+    PCD_CUDA(cudaEventSynchronize(ctx->events[slot_stop]));
+    float ms = 0.f;
+    PCD_CUDA(cudaEventElapsedTime(&ms, ctx->events[slot_start], ctx->events[slot_stop]));
+    *ms_out = ms;
+    return PCD_OK;
+}
+
+int pcd_flush_l2(pcd_ctx *ctx) {
+    NEED_CTX(ctx);
+    const size_t bytes = 256u << 20;
+    if (!ctx->l2_scratch) PCD_CUDA(cudaMalloc(&ctx->l2_scratch, bytes));
+    PCD_CUDA(cudaMemsetAsync(ctx->l2_scratch, 0x5a, bytes, ctx->stream));
+    return PCD_OK;
+}
+
 // ---- poisson_solver ------------------------------------------------------------------------------
 int pcd_solver_create(int width, int height, int device, int solver_path, pcd_solver **out) {
     if (!out) { set_error("null argument"); return PCD_ERR_INVALID; }
@@ -304,6 +341,7 @@ int pcd_solver_create(int width, int height, int device, int solver_path, pcd_so
         if (e == cudaSuccess) e = cudaMalloc(&s->phi, sizeof(double) * n);
         if (e == cudaSuccess) e = cudaMemset(s->D, 0, sizeof(double) * n);
         if (e == cudaSuccess) e = cudaMemset(s->phi, 0, sizeof(double) * n);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();  // zero-fills ran on the legacy default stream
         s->own_fields = true;
         if (e != cudaSuccess) { set_error("solver allocation failed: %s", cudaGetErrorString(e)); rc = PCD_ERR_CUDA; }
     }

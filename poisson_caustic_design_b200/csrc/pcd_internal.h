@@ -74,7 +74,7 @@ struct pcd_solver {
     int res_ctas = 0, res_threads = 0, res_rows_per_cta = 0;
     size_t res_smem = 0;
     int sm_count = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
 };
 
 namespace pcd {
@@ -113,9 +113,22 @@ struct pcd_ctx {
     int *d_flags = nullptr, *h_flags = nullptr;
     pcd_solver solver;
     pcd_solve_info last{};
+    pcd_solve_info totals{};
+    cudaEvent_t events[8] = {};
+    void *l2_scratch = nullptr;
 };
 
 namespace pcd {
+// solve on the context's grid and fold the result into ctx->last / ctx->totals
+inline int ctx_solve(pcd_ctx *c, const double *D_dev, double *x_dev, double tol) {
+    int rc = solver_run(&c->solver, D_dev, x_dev, 100000, tol, &c->last);  // cap 100000: src/caustic_design.cpp:222,311
+    c->totals.sweeps += c->last.sweeps;
+    c->totals.launches += c->last.launches;
+    c->totals.kernel_ms += c->last.kernel_ms;
+    c->totals.device_ms += c->last.device_ms;
+    c->totals.path = c->last.path;
+    return rc;
+}
 // init_kernels.cu
 int k_init(pcd_ctx *c, const double *image_host);
 // transport_kernels.cu

@@ -124,6 +124,7 @@ static int run_streaming(pcd_solver *s, const double *D, double *phi, int max_it
     while (done < max_it && !conv) {
         const int k = max_it - done < chunk ? max_it - done : chunk;
         PCD_CUDA(cudaMemsetAsync(s->sweep_max, 0, sizeof(unsigned long long) * k, s->stream));
+        PCD_CUDA(cudaEventRecord(s->evk0, s->stream));
         for (int j = 0; j < k; ++j)
             for (int colour = 0; colour < 2; ++colour) {
                 if (masked)
@@ -133,8 +134,14 @@ static int run_streaming(pcd_solver *s, const double *D, double *phi, int max_it
                 PCD_LAUNCHED();
                 info->launches++;
             }
+        PCD_CUDA(cudaEventRecord(s->evk1, s->stream));
         PCD_CUDA(cudaMemcpyAsync(s->h_sweep_max, s->sweep_max, sizeof(unsigned long long) * k, cudaMemcpyDeviceToHost, s->stream));
         PCD_CUDA(cudaStreamSynchronize(s->stream));
+        {
+            float kms = 0.f;
+            PCD_CUDA(cudaEventElapsedTime(&kms, s->evk0, s->evk1));
+            info->kernel_ms += kms;
+        }
         for (int j = 0; j < k; ++j) {
             double m;
             memcpy(&m, &s->h_sweep_max[j], sizeof(double));
@@ -441,16 +448,23 @@ static int run_resident(pcd_solver *s, const double *D, double *phi, int max_it,
         prm.P = P; prm.max_it = k; prm.lag = lag; prm.tol = tol; prm.w = make_w(W);
         prm.ll = (uint4 *)s->halo; prm.g_max = g_max; prm.g_cnt = g_cnt; prm.state = (ResState *)s->res_state;
         int rc;
+        PCD_CUDA(cudaEventRecord(s->evk0, s->stream));
         switch (s->res_threads) {
             case 2: rc = launch_resident<2>(s, prm); break;
             case 4: rc = launch_resident<4>(s, prm); break;
             default: rc = launch_resident<8>(s, prm); break;
         }
         PCD_TRY(rc);
+        PCD_CUDA(cudaEventRecord(s->evk1, s->stream));
         info->launches++;
         PCD_CUDA(cudaMemcpyAsync(s->h_res_state, s->res_state, sizeof(ResState), cudaMemcpyDeviceToHost, s->stream));
         PCD_CUDA(cudaStreamSynchronize(s->stream));
         const ResState st = *(ResState *)s->h_res_state;
+        {
+            float kms = 0.f;
+            PCD_CUDA(cudaEventElapsedTime(&kms, s->evk0, s->evk1));
+            info->kernel_ms += kms;
+        }
         // the device acts on the test with a lag: when the cap ends the launch, the last lag+1 sweeps
         // were executed but never tested -- scan them here so converged_at is exact
         int conv_local = st.converged_at;
@@ -500,6 +514,8 @@ int solver_init(pcd_solver *s, int W, int H, int device, int path, cudaStream_t 
     PCD_CUDA(cudaMallocHost(&s->h_res_state, sizeof(ResState)));
     PCD_CUDA(cudaEventCreate(&s->ev0));
     PCD_CUDA(cudaEventCreate(&s->ev1));
+    PCD_CUDA(cudaEventCreate(&s->evk0));
+    PCD_CUDA(cudaEventCreate(&s->evk1));
     s->path_used = PCD_SOLVER_STREAMING;
     if (path != PCD_SOLVER_STREAMING) {
         int coop = 0;
@@ -523,6 +539,8 @@ void solver_free(pcd_solver *s) {
     if (s->own_fields) { cudaFree(s->D); cudaFree(s->phi); }
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->evk0) cudaEventDestroy(s->evk0);
+    if (s->evk1) cudaEventDestroy(s->evk1);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     *s = pcd_solver();
 }
