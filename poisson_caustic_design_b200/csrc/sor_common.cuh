@@ -1,0 +1,45 @@
+// Shared between the streaming (sor_kernels.cu) and resident (sor_resident.cu) K-SOR kernels.
+#pragma once
+
+#include "pcd_internal.h"
+
+namespace pcd {
+
+struct SorW {
+    double w[5];  // omega / cnt, cnt = 0..4 (w[0] = +inf as in the reference's division)
+};
+
+inline SorW make_w(int W) {
+    SorW r;
+    double omega = sor_omega(W);
+    for (int c = 0; c < 5; ++c) r.w[c] = omega / (double)c;
+    return r;
+}
+
+__device__ __forceinline__ double wsel(const SorW &w, int cnt) {
+    return cnt == 4 ? w.w[4] : (cnt == 3 ? w.w[3] : (cnt == 2 ? w.w[2] : (cnt == 1 ? w.w[1] : w.w[0])));
+}
+
+__device__ __forceinline__ double warp_max(double a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double b = __shfl_xor_sync(0xffffffffu, a, o);
+        a = b > a ? b : a;
+    }
+    return a;
+}
+
+
+constexpr int RES_MAX_SWEEPS_PER_LAUNCH = 1 << 17;
+
+struct ResState {  // device control block of the resident kernel (mirrored in pinned host memory)
+    int sweeps;
+    int converged_at;
+    int pad0, pad1;
+};
+
+// sor_resident.cu
+int resident_plan(pcd_solver *s);   // 1 when the grid fits the on-chip path (fills s->res_*)
+int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double tol, pcd_solve_info *info);
+
+}  // namespace pcd

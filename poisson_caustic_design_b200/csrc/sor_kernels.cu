@@ -17,37 +17,9 @@
 //                 messages, so there is no grid-wide barrier and no fence on the critical path; the
 //                 convergence test is a per-sweep atomicMax + arrival counter evaluated with a fixed
 //                 lag by a dedicated control warp.
-#include "pcd_internal.h"
-
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
+#include "sor_common.cuh"
 
 namespace pcd {
-
-struct SorW {
-    double w[5];  // omega / cnt, cnt = 0..4 (w[0] = +inf as in the reference's division)
-};
-
-static SorW make_w(int W) {
-    SorW r;
-    double omega = sor_omega(W);
-    for (int c = 0; c < 5; ++c) r.w[c] = omega / (double)c;
-    return r;
-}
-
-__device__ __forceinline__ double wsel(const SorW &w, int cnt) {
-    return cnt == 4 ? w.w[4] : (cnt == 3 ? w.w[3] : (cnt == 2 ? w.w[2] : (cnt == 1 ? w.w[1] : w.w[0])));
-}
-
-__device__ __forceinline__ double warp_max(double a) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double b = __shfl_xor_sync(0xffffffffu, a, o);
-        a = b > a ? b : a;
-    }
-    return a;
-}
 
 // ------------------------------------------------------------------------------------------------
 // neighbour masks (bit0 left, bit1 up, bit2 right, bit3 down), only needed when D has NaN holes
@@ -160,332 +132,6 @@ static int run_streaming(pcd_solver *s, const double *D, double *phi, int max_it
 }
 
 // ------------------------------------------------------------------------------------------------
-// resident path
-// ------------------------------------------------------------------------------------------------
-constexpr int RES_COMPUTE_THREADS = 480;  // 15 warps + 1 control warp = 16 warps = 4 per SM sub-partition (128 regs each)
-constexpr int RES_THREADS = RES_COMPUTE_THREADS + 32;  // + control warp
-constexpr int RES_MAX_SWEEPS_PER_LAUNCH = 1 << 17;
-
-struct ResState {  // device control block (also mirrored in pinned host memory)
-    int sweeps;
-    int converged_at;
-    int pad0, pad1;
-};
-
-struct ResParams {
-    double *phi;              // global field, in/out
-    const double *D;
-    int W, H, K, Kp;          // K = ceil(W/2) column pairs per row, Kp = padded pitch (doubles) of one parity array
-    int P;                    // CTAs
-    int max_it;               // sweeps this launch may execute
-    int lag;                  // convergence lag L
-    double tol;
-    SorW w;
-    uint4 *ll;                // LL halo slots: [P][2][W] x 16 B
-    unsigned long long *g_max;  // [max_it]
-    unsigned int *g_cnt;        // [max_it]
-    ResState *state;
-};
-
-__device__ __forceinline__ void ll_store(uint4 *p, double v, unsigned seq) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"(seq),
-                 "r"((unsigned)(b >> 32)), "r"(seq)
-                 : "memory");
-}
-
-__device__ __forceinline__ double ll_wait(const uint4 *p, unsigned seq) {
-    unsigned lo, f0, hi, f1;
-    do {
-        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(p) : "memory");
-    } while (f0 != seq || f1 != seq);
-    return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
-}
-
-__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-// One item = the column pair (2k, 2k+1) of one slab row; exactly one of its two cells is updated per
-// colour phase.  Everything that is invariant across sweeps sits in registers.
-template <int MAXI>
-__global__ void __launch_bounds__(RES_THREADS, 1) sor_resident_kernel(ResParams p) {
-    extern __shared__ double smem[];
-    __shared__ unsigned long long blkmax[2];
-    __shared__ int s_stop_after;  // number of sweeps after which every CTA leaves the loop (0 = keep going)
-
-    const int tid = threadIdx.x;
-    const int cta = blockIdx.x;
-    const int W = p.W, H = p.H, K = p.K, Kp = p.Kp;
-    const int r0 = (int)(((long long)cta * H) / p.P), r1 = (int)(((long long)(cta + 1) * H) / p.P);
-    const int nr = r1 - r0;
-    // smem: local row ly in [0, nr+2) (ly = 0 / nr+1 are the halo rows), parity q in {0,1}:
-    //   sm[(ly*2 + q)*Kp + 1 + k]   (+1: one pad double in front so that k-1 = -1 is addressable)
-    double *sm = smem;
-    auto sidx = [Kp](int ly, int q, int k) { return (ly * 2 + q) * Kp + 1 + k; };
-
-    if (tid == 0) {
-        blkmax[0] = 0ull;
-        blkmax[1] = 0ull;
-        s_stop_after = 0;
-    }
-
-    const bool is_compute = tid < RES_COMPUTE_THREADS;
-    // ---- per-item invariants ---------------------------------------------------------------
-    // packed per item: bits 0-7 local row ly (1..nr, 0 = unused) | bits 8-19 flags m | bits 20-31 column pair k
-    //   m: bits 0-3 neighbour mask of cell 0 (x = 2k), 4-7 of cell 1, 8/9 cell valid, 10 top row, 11 bottom row
-    unsigned it_meta[MAXI];
-    double it_D[MAXI][2], it_v[MAXI][2];
-#pragma unroll
-    for (int j = 0; j < MAXI; ++j) {
-        it_meta[j] = 0;
-        it_D[j][0] = it_D[j][1] = it_v[j][0] = it_v[j][1] = 0.0;
-        const int id = tid + j * RES_COMPUTE_THREADS;
-        if (is_compute && id < nr * K) {
-            const int ro = id / K, k = id - ro * K;
-            // row order: top boundary row, bottom boundary row, then the interior rows
-            const int ly = ro == 0 ? 1 : (ro == 1 ? nr : ro);
-            const int y = r0 + ly - 1;
-            unsigned m = 0;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int x = 2 * k + q;
-                if (x < W) {
-                    const size_t i = (size_t)y * W + x;
-                    unsigned mm = 0;
-                    if (x != 0 && !isnan(p.D[i - 1])) mm |= 1;
-                    if (y != 0 && !isnan(p.D[i - W])) mm |= 2;
-                    if (x != W - 1 && !isnan(p.D[i + 1])) mm |= 4;
-                    if (y != H - 1 && !isnan(p.D[i + W])) mm |= 8;
-                    m |= mm << (4 * q);
-                    m |= 1u << (8 + q);
-                    it_D[j][q] = p.D[i];
-                    it_v[j][q] = p.phi[i];
-                    sm[sidx(ly, q, k)] = it_v[j][q];
-                }
-            }
-            if (ly == 1) m |= 1u << 10;
-            if (ly == nr) m |= 1u << 11;
-            it_meta[j] = (unsigned)ly | (m << 8) | ((unsigned)k << 20);
-        }
-    }
-    // halo rows from the global field (state before the first phase)
-    if (is_compute) {
-        for (int k = tid; k < K; k += RES_COMPUTE_THREADS)
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int x = 2 * k + q;
-                if (x < W) {
-                    if (r0 > 0) sm[sidx(0, q, k)] = p.phi[(size_t)(r0 - 1) * W + x];
-                    if (r1 < H) sm[sidx(nr + 1, q, k)] = p.phi[(size_t)r1 * W + x];
-                }
-            }
-    }
-    __syncthreads();
-
-    uint4 *ll_up = cta > 0 ? p.ll + ((size_t)(cta - 1) * 2 + 1) * W : nullptr;      // neighbour above: its "from below" slots
-    uint4 *ll_dn = cta + 1 < p.P ? p.ll + ((size_t)(cta + 1) * 2 + 0) * W : nullptr;  // neighbour below: its "from above" slots
-    const uint4 *ll_in_top = p.ll + ((size_t)cta * 2 + 0) * W;
-    const uint4 *ll_in_bot = p.ll + ((size_t)cta * 2 + 1) * W;
-
-    const int max_it = p.max_it;
-    int s = 0;
-    if (is_compute) {
-        // =============================== compute warps ===========================================
-        for (;; ++s) {
-            double lmax = 0.0;
-#pragma unroll
-            for (int colour = 0; colour < 2; ++colour) {
-                const unsigned seq = 2u * (unsigned)s + (unsigned)colour + 1u;
-#pragma unroll
-                for (int j = 0; j < MAXI; ++j) {
-                    const int ly = (int)(it_meta[j] & 255u);
-                    if (ly == 0) continue;
-                    const int k = (int)(it_meta[j] >> 20);
-                    const int y = r0 + ly - 1;
-                    const int q = (y + colour) & 1;  // column parity of this row's active cell
-                    const unsigned m = (it_meta[j] >> 8) & 0xfffu;
-                    if (!((m >> (8 + q)) & 1u)) continue;
-                    const unsigned mm = (m >> (4 * q)) & 15u;
-                    // neighbours: left/right live in the other parity array of the same row
-                    const int kl = q ? k : k - 1, kr = q ? k + 1 : k;
-                    const double vl = (mm & 1) ? sm[sidx(ly, q ^ 1, kl)] : 0.0;
-                    const double vu = (mm & 2) ? sm[sidx(ly - 1, q, k)] : 0.0;
-                    const double vr = (mm & 4) ? sm[sidx(ly, q ^ 1, kr)] : 0.0;
-                    const double vd = (mm & 8) ? sm[sidx(ly + 1, q, k)] : 0.0;
-                    double sum = 0.0;
-                    if (mm & 1) sum += vl;
-                    if (mm & 2) sum += vu;
-                    if (mm & 4) sum += vr;
-                    if (mm & 8) sum += vd;
-                    const int cnt = __popc(mm);
-                    const double val = q ? it_v[j][1] : it_v[j][0];
-                    const double Dv = q ? it_D[j][1] : it_D[j][0];
-                    const double delta = wsel(p.w, cnt) * (sum - (double)cnt * val - Dv);
-                    const double ad = fabs(delta);
-                    if (ad > lmax) lmax = ad;
-                    const double nv = val + delta;
-                    if (q) it_v[j][1] = nv; else it_v[j][0] = nv;
-                    sm[sidx(ly, q, k)] = nv;
-                    const int x = 2 * k + q;
-                    if ((m & (1u << 10)) && ll_up) ll_store(ll_up + x, nv, seq);
-                    if ((m & (1u << 11)) && ll_dn) ll_store(ll_dn + x, nv, seq);
-                }
-                // import the neighbours' boundary cells of this colour (produced in their phase `seq`)
-                for (int k = tid; k < K; k += RES_COMPUTE_THREADS) {
-                    if (cta > 0) {
-                        const int q = (r0 - 1 + colour) & 1, x = 2 * k + q;
-                        if (x < W) sm[sidx(0, q, k)] = ll_wait(ll_in_top + x, seq);
-                    }
-                    if (cta + 1 < p.P) {
-                        const int q = (r1 + colour) & 1, x = 2 * k + q;
-                        if (x < W) sm[sidx(nr + 1, q, k)] = ll_wait(ll_in_bot + x, seq);
-                    }
-                }
-                if (colour == 0) {
-                    bar_sync(1, RES_COMPUTE_THREADS);  // compute warps only
-                } else {
-                    lmax = warp_max(lmax);
-                    if ((tid & 31) == 0 && lmax > 0.0)
-                        atomicMax(&blkmax[s & 1], (unsigned long long)__double_as_longlong(lmax));
-                    bar_sync(0, RES_THREADS);          // end of sweep, with the control warp
-                }
-            }
-            const int stop = s_stop_after;
-            if (stop == s + 1 || s + 1 >= max_it) break;
-        }
-        // ---- write the slab back ----------------------------------------------------------------
-#pragma unroll
-        for (int j = 0; j < MAXI; ++j) {
-            const int ly = (int)(it_meta[j] & 255u);
-            if (ly == 0) continue;
-            const int y = r0 + ly - 1, k = (int)(it_meta[j] >> 20);
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-                if ((it_meta[j] >> (16 + q)) & 1u) p.phi[(size_t)y * W + 2 * k + q] = it_v[j][q];
-        }
-    } else {
-        // =============================== control warp =============================================
-        const int lane = tid & 31;
-        int conv_at = 0;
-        for (;; ++s) {
-            bar_sync(0, RES_THREADS);  // end of sweep s
-            const int stop = s_stop_after;
-            if (lane == 0) {
-                const unsigned long long bm = blkmax[s & 1];
-                blkmax[s & 1] = 0ull;
-                if (bm) atomicMax(p.g_max + s, bm);
-                __threadfence();
-                atomicAdd(p.g_cnt + s, 1u);
-            }
-            if (stop == s + 1 || s + 1 >= max_it) break;
-            // evaluate sweep e = s - lag: acted on by everybody after sweep s+1
-            const int e = s - p.lag;
-            if (lane == 0 && e >= 0 && conv_at == 0) {
-                const volatile unsigned int *c = p.g_cnt + e;
-                while (*c != (unsigned)p.P) { }
-                __threadfence();
-                const unsigned long long bits = *((const volatile unsigned long long *)(p.g_max + e));
-                if (__longlong_as_double((long long)bits) < p.tol) {
-                    conv_at = e + 1;
-                    s_stop_after = s + 2;
-                }
-            }
-        }
-        // tail: sweeps whose convergence test was never acted on still have to be scanned by the host
-        if (lane == 0 && cta == 0) {
-            p.state->sweeps = s + 1;
-            p.state->converged_at = conv_at;
-        }
-    }
-}
-
-static size_t resident_smem_bytes(int nr_max, int Kp) { return (size_t)(nr_max + 2) * 2 * Kp * sizeof(double); }
-
-static int resident_plan(pcd_solver *s) {
-    const int W = s->W, H = s->H;
-    const int P = s->sm_count < H ? s->sm_count : H;
-    const int nr_max = (H + P - 1) / P;
-    const int K = (W + 1) / 2;
-    const int Kp = ((K + 2 + 3) / 4) * 4;  // pad: 1 double in front, >=1 behind, pitch multiple of 32 B
-    const long items = (long)nr_max * K;
-    int maxi = 0;
-    if (items <= 2L * RES_COMPUTE_THREADS) maxi = 2;
-    else if (items <= 4L * RES_COMPUTE_THREADS) maxi = 4;
-    else if (items <= 8L * RES_COMPUTE_THREADS) maxi = 8;
-    const size_t smem = resident_smem_bytes(nr_max, Kp);
-    if (!maxi || smem > 200 * 1024 || nr_max > 250 || K > 4095) return 0;
-    s->res_ctas = P;
-    s->res_rows_per_cta = nr_max;
-    s->res_smem = smem;
-    s->res_threads = maxi;  // reused: items per thread
-    return 1;
-}
-
-template <int MAXI>
-static int launch_resident(pcd_solver *s, ResParams &prm) {
-    PCD_CUDA(cudaFuncSetAttribute(sor_resident_kernel<MAXI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->res_smem));
-    void *args[] = {&prm};
-    PCD_CUDA(cudaLaunchCooperativeKernel((void *)sor_resident_kernel<MAXI>, dim3(s->res_ctas), dim3(RES_THREADS), args,
-                                         s->res_smem, s->stream));
-    PCD_LAUNCHED();
-    return PCD_OK;
-}
-
-static int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double tol, pcd_solve_info *info) {
-    const int W = s->W, H = s->H;
-    const int P = s->res_ctas;
-    const int lag = s->check_lag > 0 ? s->check_lag : 4;
-    int done = 0, conv = 0;
-    double last = 0.0;
-    unsigned long long *g_max = s->sweep_max;
-    unsigned int *g_cnt = (unsigned int *)(s->sweep_max + s->ring);
-    while (done < max_it && !conv) {
-        const int k = max_it - done < RES_MAX_SWEEPS_PER_LAUNCH ? max_it - done : RES_MAX_SWEEPS_PER_LAUNCH;
-        PCD_CUDA(cudaMemsetAsync(s->sweep_max, 0, (sizeof(unsigned long long) + sizeof(unsigned int)) * (size_t)s->ring, s->stream));
-        PCD_CUDA(cudaMemsetAsync(s->halo, 0, (size_t)P * 2 * W * sizeof(uint4), s->stream));
-        ResParams prm;
-        prm.phi = phi; prm.D = D; prm.W = W; prm.H = H; prm.K = (W + 1) / 2;
-        prm.Kp = ((prm.K + 2 + 3) / 4) * 4;
-        prm.P = P; prm.max_it = k; prm.lag = lag; prm.tol = tol; prm.w = make_w(W);
-        prm.ll = (uint4 *)s->halo; prm.g_max = g_max; prm.g_cnt = g_cnt; prm.state = (ResState *)s->res_state;
-        int rc;
-        PCD_CUDA(cudaEventRecord(s->evk0, s->stream));
-        switch (s->res_threads) {
-            case 2: rc = launch_resident<2>(s, prm); break;
-            case 4: rc = launch_resident<4>(s, prm); break;
-            default: rc = launch_resident<8>(s, prm); break;
-        }
-        PCD_TRY(rc);
-        PCD_CUDA(cudaEventRecord(s->evk1, s->stream));
-        info->launches++;
-        PCD_CUDA(cudaMemcpyAsync(s->h_res_state, s->res_state, sizeof(ResState), cudaMemcpyDeviceToHost, s->stream));
-        PCD_CUDA(cudaStreamSynchronize(s->stream));
-        const ResState st = *(ResState *)s->h_res_state;
-        {
-            float kms = 0.f;
-            PCD_CUDA(cudaEventElapsedTime(&kms, s->evk0, s->evk1));
-            info->kernel_ms += kms;
-        }
-        // the device acts on the test with a lag: when the cap ends the launch, the last lag+1 sweeps
-        // were executed but never tested -- scan them here so converged_at is exact
-        int conv_local = st.converged_at;
-        const int first = conv_local ? conv_local - 1 : (st.sweeps - (lag + 2) > 0 ? st.sweeps - (lag + 2) : 0);
-        const int cnt = conv_local ? 1 : st.sweeps - first;
-        PCD_CUDA(cudaMemcpyAsync(s->h_sweep_max, g_max + first, sizeof(unsigned long long) * cnt, cudaMemcpyDeviceToHost, s->stream));
-        PCD_CUDA(cudaStreamSynchronize(s->stream));
-        for (int j = 0; j < cnt; ++j) {
-            memcpy(&last, &s->h_sweep_max[j], sizeof(double));
-            if (!conv_local && last < tol) { conv_local = first + j + 1; break; }
-        }
-        if (conv_local) conv = done + conv_local;
-        done += st.sweeps;
-    }
-    info->sweeps = done;
-    info->converged_at = conv;
-    info->last_max_update = last;
-    return PCD_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
 // solver object
 // ------------------------------------------------------------------------------------------------
 int solver_init(pcd_solver *s, int W, int H, int device, int path, cudaStream_t stream) {
@@ -506,7 +152,7 @@ int solver_init(pcd_solver *s, int W, int H, int device, int path, cudaStream_t 
         s->own_stream = true;
     }
     s->ring = RES_MAX_SWEEPS_PER_LAUNCH;
-    PCD_CUDA(cudaMalloc(&s->sweep_max, (sizeof(unsigned long long) + sizeof(unsigned int)) * (size_t)s->ring));
+    PCD_CUDA(cudaMalloc(&s->sweep_max, 2 * sizeof(unsigned long long) * (size_t)s->ring));  // per-sweep max + arrival slot
     PCD_CUDA(cudaMallocHost(&s->h_sweep_max, sizeof(unsigned long long) * 4096));
     PCD_CUDA(cudaMalloc(&s->d_flags, sizeof(int) * 4));
     PCD_CUDA(cudaMallocHost(&s->h_flags, sizeof(int) * 4));

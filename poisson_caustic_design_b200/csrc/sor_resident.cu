@@ -1,0 +1,390 @@
+// K-SOR, resident path: ONE persistent cooperative kernel per Poisson solve (sm_100a).
+//
+// Decomposition: CTA c (one per SM, co-resident by cooperative launch) owns NR consecutive grid rows
+// [c*NR, c*NR+NR); thread k of its 512 threads owns the column pair (2k, 2k+1) of every one of those
+// rows -- a vertical strip of 2*NR cells whose phi and D values stay in REGISTERS for the whole solve.
+//   * up / down neighbours of a cell are the thread's own registers (compile-time indices);
+//   * the left / right neighbour that belongs to thread k-1 / k+1 goes through shared memory
+//     (one STS + one LDS per cell update, unit stride, conflict-free);
+//   * the rows above / below the slab belong to the neighbouring CTAs: each boundary cell is pushed to
+//     the neighbour through L2 as one 16-byte flag-in-data message {lo, seq, hi, seq} ("LL" protocol:
+//     each 8-byte half is written atomically and carries the phase number, so the reader needs no
+//     fence and no separate flag) and is polled by exactly the thread that consumes it -> registers.
+//     There is no grid-wide barrier; CTAs only ever wait for their two neighbours.
+//   * convergence: per sweep every CTA adds (1 | not_converged<<32) to that sweep's slot with ONE
+//     atomic (arrival count and verdict travel together, no fence); the slot of sweep s-lag is read at
+//     the end of sweep s by thread 0 of every CTA, so all CTAs leave after the same sweep.
+// Domain edges cost nothing in the hot loop: a missing neighbour reads a 0.0 ghost (x + 0.0 == x, so the
+// reference's "skip the neighbour" sum is reproduced bit for bit) and the per-cell neighbour count /
+// omega/cnt factors are per-thread registers selected at compile time by (row class, column parity).
+// Threads whose strip touches NaN holes, phantom cells (odd W, short last slab) run a per-cell masked path.
+//
+// Update formula, ordering and stopping rule: src/solver.cpp:12-61,70-147 (see sor_kernels.cu header).
+#include "sor_common.cuh"
+
+namespace pcd {
+
+constexpr int RES_NT = 512;     // 16 warps = 4 per SM sub-partition -> 128 registers per thread
+constexpr int RES_NR_MAX = 7;   // rows per slab (2*NR phi + 2*NR D doubles per thread)
+constexpr int RES_KP = RES_NT + 4;  // smem pitch of one parity row: compile-time so every smem offset is an immediate
+
+struct ResParams {
+    double *phi;              // global field, in/out
+    const double *D;
+    int W, H, K, Kp;          // K = ceil(W/2) column pairs per row, Kp = padded pitch of one parity row in smem
+    int P;                    // CTAs
+    int max_it;               // sweeps this launch may execute
+    int lag;                  // convergence lag
+    double tol;
+    SorW w;
+    uint4 *ll;                // LL halo slots: [P][2][W] x 16 B  ([.][0] = from the CTA above, [.][1] = from below)
+    unsigned long long *g_max;   // [max_it] per-sweep max|delta| bit patterns
+    unsigned long long *g_slot;  // [max_it] low 32: CTAs arrived, high 32: CTAs whose max >= tol
+    ResState *state;
+};
+
+__device__ __forceinline__ void ll_store(uint4 *p, double v, unsigned seq) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"(seq),
+                 "r"((unsigned)(b >> 32)), "r"(seq)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint4 ll_issue(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
+__device__ __forceinline__ double ll_consume(uint4 r, const uint4 *p, unsigned seq) {
+    while (r.y != seq || r.w != seq) r = ll_issue(p);
+    return __longlong_as_double((long long)(((unsigned long long)r.z << 32) | r.x));
+}
+
+// Per-thread strip state.
+template <int NR>
+struct Strip {
+    double v[NR][2];   // phi of (row j, column 2k+q)
+    double D[NR][2];
+    // neighbour count and omega/cnt by row class (T = row 0, M = rows 1..NR-2, B = row NR-1) and parity
+    double cT[2], cM[2], cB[2], wT[2], wM[2], wB[2];
+    unsigned long long masks;  // 4-bit neighbour mask per cell at bit 8j+4q (bit0 left, 1 up, 2 right, 3 down)
+    unsigned valid;            // bit 2j+q
+};
+
+// Update of the active cell of row J in a colour phase.  P0 = column parity of the active cell of row 0;
+// row j's active cell has parity (P0+j)&1.
+template <int NR, int P0, bool FAST, bool EDGE, int J>
+__device__ __forceinline__ void res_cell(Strip<NR> &s, double *__restrict__ smk, const int /*Kp*/, const double hu,
+                                         const double hd, const ResParams &p, double &lmax, const int k,
+                                         uint4 *ll_up, uint4 *ll_dn, const unsigned seq) {
+    constexpr int j = J;
+    constexpr int q = (P0 + j) & 1;
+    constexpr int Kp = RES_KP;
+    // the one neighbour owned by another thread: left (q = 0) or right (q = 1), other parity row in smem
+    const double nb = (q == 0) ? smk[(j * 2 + 1) * Kp - 1] : smk[(j * 2 + 0) * Kp + 1];
+    const double own = s.v[j][q ^ 1];
+    const double l = (q == 0) ? nb : own, r = (q == 0) ? own : nb;
+    const double u = (j == 0) ? hu : s.v[(j == 0) ? 0 : j - 1][q];
+    const double d = (j == NR - 1) ? hd : s.v[(j == NR - 1) ? j : j + 1][q];
+    const double val = s.v[j][q];
+    double nv;
+    if (FAST) {
+        // only the first / last slab (EDGE) has rows whose neighbour count differs from the interior rows'
+        const double cnt = (EDGE && j == 0) ? s.cT[q] : ((EDGE && j == NR - 1) ? s.cB[q] : s.cM[q]);
+        const double wv = (EDGE && j == 0) ? s.wT[q] : ((EDGE && j == NR - 1) ? s.wB[q] : s.wM[q]);
+        const double sum = ((l + u) + r) + d;  // ghosts are 0.0: identical to skipping them
+        const double delta = wv * ((sum - cnt * val) - s.D[j][q]);
+        const double ad = fabs(delta);
+        if (ad > lmax) lmax = ad;
+        nv = val + delta;
+    } else {
+        if (!((s.valid >> (2 * j + q)) & 1u)) return;
+        const unsigned mm = (unsigned)(s.masks >> (8 * j + 4 * q)) & 15u;
+        double sum = 0.0;
+        if (mm & 1) sum += l;
+        if (mm & 2) sum += u;
+        if (mm & 4) sum += r;
+        if (mm & 8) sum += d;
+        const int cnt = __popc(mm);
+        const double delta = wsel(p.w, cnt) * (sum - (double)cnt * val - s.D[j][q]);
+        const double ad = fabs(delta);
+        if (ad > lmax) lmax = ad;
+        nv = val + delta;
+    }
+    s.v[j][q] = nv;
+    smk[(j * 2 + q) * Kp] = nv;
+    if (j == 0 && ll_up) ll_store(ll_up + 2 * k + q, nv, seq);
+    if (j == NR - 1 && ll_dn) ll_store(ll_dn + 2 * k + q, nv, seq);
+}
+
+template <int NR, int P0, bool FAST, bool EDGE, int J>
+struct InteriorRows {  // rows J .. NR-2 (compile-time recursion keeps every register index static)
+    static __device__ __forceinline__ void run(Strip<NR> &s, double *__restrict__ smk, const int Kp, const ResParams &p,
+                                               double &lmax, const int k, const unsigned seq) {
+        if constexpr (J <= NR - 2) {
+            res_cell<NR, P0, FAST, EDGE, J>(s, smk, Kp, 0.0, 0.0, p, lmax, k, nullptr, nullptr, seq);
+            InteriorRows<NR, P0, FAST, EDGE, J + 1>::run(s, smk, Kp, p, lmax, k, seq);
+        }
+    }
+};
+
+// One colour phase of one slab: interior rows first (they need nothing from other CTAs), then the halo
+// messages of the previous phase are consumed and the two boundary rows are updated and exported -- so a
+// message is in flight while both CTAs work on their interiors.
+template <int NR, int P0, bool FAST, bool EDGE>
+__device__ __forceinline__ void res_phase(Strip<NR> &s, double *__restrict__ smk, const int Kp, double &hu, double &hd,
+                                          const ResParams &p, double &lmax, const int k, uint4 *ll_up, uint4 *ll_dn,
+                                          const unsigned seq, const uint4 *in_t, const uint4 *in_b, const bool first) {
+    uint4 rt = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+    if (!first) {  // polls for the cells the neighbours produced in their previous phase (seq-1)
+        if (in_t) rt = ll_issue(in_t);
+        if (in_b) rb = ll_issue(in_b);
+    }
+    InteriorRows<NR, P0, FAST, EDGE, 1>::run(s, smk, Kp, p, lmax, k, seq);
+    if (!first) {
+        if (in_t) hu = ll_consume(rt, in_t, seq - 1u);
+        if (in_b) hd = ll_consume(rb, in_b, seq - 1u);
+    }
+    res_cell<NR, P0, FAST, EDGE, 0>(s, smk, Kp, hu, hd, p, lmax, k, ll_up, ll_dn, seq);
+    if constexpr (NR >= 2) res_cell<NR, P0, FAST, EDGE, NR - 1>(s, smk, Kp, hu, hd, p, lmax, k, ll_up, ll_dn, seq);
+}
+
+template <int NR, bool EDGE>
+__device__ __forceinline__ void res_body(const ResParams &p) {
+    extern __shared__ double smem[];  // [NR][2][Kp], element (j, q, k) at (j*2+q)*Kp + 1 + k; pads stay 0.0
+    __shared__ unsigned long long blkmax[2];
+    __shared__ int s_stop;
+
+    const int tid = threadIdx.x, cta = blockIdx.x, k = tid;
+    const int W = p.W, H = p.H, K = p.K;
+    constexpr int Kp = RES_KP;
+    const int r0 = cta * NR;
+    const bool has_up = cta > 0, has_dn = cta + 1 < p.P;
+
+    for (int i = tid; i < NR * 2 * Kp; i += RES_NT) smem[i] = 0.0;
+    if (tid == 0) { blkmax[0] = 0ull; blkmax[1] = 0ull; s_stop = 0; }
+    __syncthreads();
+
+    // ---- load the strip -----------------------------------------------------------------------
+    Strip<NR> s;
+    s.masks = 0ull;
+    s.valid = 0u;
+    bool fast = NR >= 2;
+#pragma unroll
+    for (int j = 0; j < NR; ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int x = 2 * k + q, y = r0 + j;
+            s.v[j][q] = 0.0;
+            s.D[j][q] = 0.0;
+            if (k < K && x < W && y < H) {
+                const size_t i = (size_t)y * W + x;
+                unsigned geo = (x != 0 ? 1u : 0u) | (y != 0 ? 2u : 0u) | (x != W - 1 ? 4u : 0u) | (y != H - 1 ? 8u : 0u);
+                unsigned mm = 0;
+                if ((geo & 1) && !isnan(p.D[i - 1])) mm |= 1;
+                if ((geo & 2) && !isnan(p.D[i - W])) mm |= 2;
+                if ((geo & 4) && !isnan(p.D[i + 1])) mm |= 4;
+                if ((geo & 8) && !isnan(p.D[i + W])) mm |= 8;
+                if (mm != geo) fast = false;
+                s.masks |= (unsigned long long)mm << (8 * j + 4 * q);
+                s.valid |= 1u << (2 * j + q);
+                s.D[j][q] = p.D[i];
+                s.v[j][q] = p.phi[i];
+                smem[(j * 2 + q) * Kp + 1 + k] = s.v[j][q];
+            } else {
+                fast = false;
+            }
+        }
+    const bool idle = s.valid == 0u;  // k >= K, or a slab without rows for this thread
+    // neighbour counts / weights by row class and parity (fast path only; geometric masks)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int cT = __popc((unsigned)(s.masks >> (4 * q)) & 15u);
+        const int cM = __popc((unsigned)(s.masks >> (8 * (NR >= 3 ? 1 : 0) + 4 * q)) & 15u);
+        const int cB = __popc((unsigned)(s.masks >> (8 * (NR - 1) + 4 * q)) & 15u);
+        s.cT[q] = (double)cT; s.cM[q] = (double)cM; s.cB[q] = (double)cB;
+        s.wT[q] = wsel(p.w, cT); s.wM[q] = wsel(p.w, cM); s.wB[q] = wsel(p.w, cB);
+    }
+
+    uint4 *ll_up = has_up ? p.ll + ((size_t)(cta - 1) * 2 + 1) * W : nullptr;   // neighbour above: its "from below" slots
+    uint4 *ll_dn = has_dn ? p.ll + ((size_t)(cta + 1) * 2 + 0) * W : nullptr;   // neighbour below: its "from above" slots
+    const uint4 *in_top = p.ll + ((size_t)cta * 2 + 0) * W;
+    const uint4 *in_bot = p.ll + ((size_t)cta * 2 + 1) * W;
+    if (idle) { ll_up = nullptr; ll_dn = nullptr; }
+    double *smk = smem + 1 + k;
+
+    // halo values for the first phase come from the global field; later ones arrive as LL messages
+    const int p0_first = r0 & 1;  // colour 0: active parity of row y is y&1
+    double hu = 0.0, hd = 0.0;
+    {
+        const int xt = 2 * k + p0_first, xb = 2 * k + ((p0_first + NR - 1) & 1);
+        if (has_up && !idle && xt < W) hu = p.phi[(size_t)(r0 - 1) * W + xt];
+        if (has_dn && !idle && xb < W) hd = p.phi[(size_t)(r0 + NR) * W + xb];
+    }
+    __syncthreads();
+
+    const int max_it = p.max_it;
+    int sweep = 0, conv_at = 0;
+    for (;; ++sweep) {
+        double lmax = 0.0;
+        unsigned long long pend = 0ull;
+        const int e = sweep - p.lag;
+        if (tid == 0 && e >= 0) pend = *((const volatile unsigned long long *)(p.g_slot + e));  // consumed at the end of the sweep
+#pragma unroll
+        for (int colour = 0; colour < 2; ++colour) {
+            const unsigned seq = 2u * (unsigned)sweep + (unsigned)colour + 1u;
+            const int p0 = (r0 + colour) & 1;
+            if (!idle) {
+                // slots of this phase's halo cells: column of the active cell of row 0 / row NR-1
+                const int xt = 2 * k + p0, xb = 2 * k + ((p0 + NR - 1) & 1);
+                const uint4 *it = (has_up && xt < W) ? in_top + xt : nullptr;
+                const uint4 *ib = (has_dn && xb < W) ? in_bot + xb : nullptr;
+                const bool first = seq == 1u;
+                if (p0 == 0) {
+                    if (fast) res_phase<NR, 0, true, EDGE>(s, smk, Kp, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
+                    else res_phase<NR, 0, false, EDGE>(s, smk, Kp, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
+                } else {
+                    if (fast) res_phase<NR, 1, true, EDGE>(s, smk, Kp, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
+                    else res_phase<NR, 1, false, EDGE>(s, smk, Kp, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
+                }
+            }
+            if (colour == 1) {
+                lmax = warp_max(lmax);
+                if ((tid & 31) == 0 && lmax > 0.0) atomicMax(&blkmax[sweep & 1], (unsigned long long)__double_as_longlong(lmax));
+                if (tid == 0 && e >= 0 && conv_at == 0) {
+                    while ((unsigned)pend != (unsigned)p.P) pend = *((const volatile unsigned long long *)(p.g_slot + e));
+                    if ((pend >> 32) == 0ull) {
+                        conv_at = e + 1;
+                        s_stop = sweep + 1;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // publish this sweep: arrival + verdict in one atomic, max separately (host reads it afterwards)
+        if (tid == 0) {
+            const unsigned long long bm = blkmax[sweep & 1];
+            blkmax[sweep & 1] = 0ull;
+            const bool below = __longlong_as_double((long long)bm) < p.tol;
+            atomicAdd(p.g_slot + sweep, 1ull | (below ? 0ull : (1ull << 32)));
+            if (bm) atomicMax(p.g_max + sweep, bm);
+        }
+        if (s_stop == sweep + 1 || sweep + 1 >= max_it) break;
+    }
+
+    // ---- write the strip back ---------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < NR; ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            if ((s.valid >> (2 * j + q)) & 1u) p.phi[(size_t)(r0 + j) * W + 2 * k + q] = s.v[j][q];
+    if (tid == 0 && cta == 0) {
+        p.state->sweeps = sweep + 1;
+        p.state->converged_at = conv_at;
+    }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(RES_NT, 1) sor_resident_kernel(const __grid_constant__ ResParams p) {
+    // the first and the last slab carry the domain's top / bottom row (different neighbour counts)
+    if (blockIdx.x == 0 || blockIdx.x + 1 == gridDim.x) res_body<NR, true>(p);
+    else res_body<NR, false>(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int resident_plan(pcd_solver *s) {
+    const int W = s->W, H = s->H;
+    const int K = (W + 1) / 2;
+    if (K > RES_NT) return 0;
+    int nr = (H + s->sm_count - 1) / s->sm_count;
+    if (nr > RES_NR_MAX) return 0;
+    // prefer a slab height whose last slab is either full (domain-bottom row stays on the fast path) or
+    // at most half full (its masked path then does not set the pace); fall back to the smallest height
+    int pick = nr;
+    for (int c = nr; c <= RES_NR_MAX; ++c) {
+        const int last = H - ((H + c - 1) / c - 1) * c;
+        if (last == c || 2 * last <= c) { pick = c; break; }
+    }
+    const int P = (H + pick - 1) / pick;
+    const int Kp = RES_KP;
+    s->res_ctas = P;
+    s->res_rows_per_cta = pick;
+    s->res_smem = (size_t)pick * 2 * Kp * sizeof(double);
+    s->res_threads = RES_NT;
+    return 1;
+}
+
+template <int NR>
+static int launch_resident(pcd_solver *s, ResParams &prm) {
+    PCD_CUDA(cudaFuncSetAttribute(sor_resident_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->res_smem));
+    void *args[] = {&prm};
+    PCD_CUDA(cudaLaunchCooperativeKernel((void *)sor_resident_kernel<NR>, dim3(s->res_ctas), dim3(RES_NT), args,
+                                         s->res_smem, s->stream));
+    PCD_LAUNCHED();
+    return PCD_OK;
+}
+
+int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double tol, pcd_solve_info *info) {
+    const int W = s->W, H = s->H;
+    const int P = s->res_ctas;
+    const int lag = s->check_lag > 0 ? s->check_lag : 4;  // >= 1: a sweep's slot is complete only after every CTA left it
+    int done = 0, conv = 0;
+    double last = 0.0;
+    unsigned long long *g_max = s->sweep_max;
+    unsigned long long *g_slot = s->sweep_max + s->ring;
+    while (done < max_it && !conv) {
+        const int k = max_it - done < RES_MAX_SWEEPS_PER_LAUNCH ? max_it - done : RES_MAX_SWEEPS_PER_LAUNCH;
+        PCD_CUDA(cudaMemsetAsync(g_max, 0, sizeof(unsigned long long) * (size_t)k, s->stream));
+        PCD_CUDA(cudaMemsetAsync(g_slot, 0, sizeof(unsigned long long) * (size_t)k, s->stream));
+        PCD_CUDA(cudaMemsetAsync(s->halo, 0, (size_t)P * 2 * W * sizeof(uint4), s->stream));
+        ResParams prm;
+        prm.phi = phi; prm.D = D; prm.W = W; prm.H = H; prm.K = (W + 1) / 2;
+        prm.Kp = RES_KP;
+        prm.P = P; prm.max_it = k; prm.lag = lag; prm.tol = tol; prm.w = make_w(W);
+        prm.ll = (uint4 *)s->halo; prm.g_max = g_max; prm.g_slot = g_slot; prm.state = (ResState *)s->res_state;
+        int rc;
+        PCD_CUDA(cudaEventRecord(s->evk0, s->stream));
+        switch (s->res_rows_per_cta) {
+            case 1: rc = launch_resident<1>(s, prm); break;
+            case 2: rc = launch_resident<2>(s, prm); break;
+            case 3: rc = launch_resident<3>(s, prm); break;
+            case 4: rc = launch_resident<4>(s, prm); break;
+            case 5: rc = launch_resident<5>(s, prm); break;
+            case 6: rc = launch_resident<6>(s, prm); break;
+            default: rc = launch_resident<7>(s, prm); break;
+        }
+        PCD_TRY(rc);
+        PCD_CUDA(cudaEventRecord(s->evk1, s->stream));
+        info->launches++;
+        PCD_CUDA(cudaMemcpyAsync(s->h_res_state, s->res_state, sizeof(ResState), cudaMemcpyDeviceToHost, s->stream));
+        PCD_CUDA(cudaStreamSynchronize(s->stream));
+        const ResState st = *(ResState *)s->h_res_state;
+        {
+            float kms = 0.f;
+            PCD_CUDA(cudaEventElapsedTime(&kms, s->evk0, s->evk1));
+            info->kernel_ms += kms;
+        }
+        // the device acts on the test with a lag: when the cap ends the launch, the last `lag` sweeps
+        // were executed but never tested -- scan them here so converged_at is exact
+        int conv_local = st.converged_at;
+        const int first = conv_local ? conv_local - 1 : (st.sweeps - (lag + 2) > 0 ? st.sweeps - (lag + 2) : 0);
+        const int cnt = conv_local ? 1 : st.sweeps - first;
+        PCD_CUDA(cudaMemcpyAsync(s->h_sweep_max, g_max + first, sizeof(unsigned long long) * cnt, cudaMemcpyDeviceToHost, s->stream));
+        PCD_CUDA(cudaStreamSynchronize(s->stream));
+        for (int j = 0; j < cnt; ++j) {
+            memcpy(&last, &s->h_sweep_max[j], sizeof(double));
+            if (!conv_local && last < tol) { conv_local = first + j + 1; break; }
+        }
+        if (conv_local) conv = done + conv_local;
+        done += st.sweeps;
+    }
+    info->sweeps = done;
+    info->converged_at = conv;
+    info->last_max_update = last;
+    return PCD_OK;
+}
+
+}  // namespace pcd

@@ -1,0 +1,120 @@
+// Microbenchmark (scratch tool): latency of CTA-to-CTA signalling through L2 on B200, the primitive under
+// the resident SOR kernel's halo exchange.  nvcc -arch=sm_100a -O3 -o ll_latency tools/ll_latency.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1);} } while (0)
+
+template <int MODE> __device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long long v) {
+    if (MODE == 0) asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    else if (MODE == 1) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    else asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+template <int MODE> __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *p) {
+    unsigned long long v;
+    if (MODE == 0) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    else if (MODE == 1) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ping-pong between CTA 0 and CTA `peer`, one thread each
+template <int MODE>
+__global__ void pingpong(unsigned long long *slots, int iters, int peer, long long *cycles) {
+    if (threadIdx.x != 0) return;
+    unsigned long long *mine = slots + 32 * blockIdx.x, *theirs;
+    if (blockIdx.x == 0) {
+        theirs = slots + 32 * peer;
+        long long t0 = clock64();
+        for (int i = 1; i <= iters; ++i) {
+            st_flag<MODE>(theirs, i);
+            while (ld_flag<MODE>(mine) != (unsigned long long)i) { }
+        }
+        *cycles = clock64() - t0;
+    } else if (blockIdx.x == peer) {
+        theirs = slots;
+        for (int i = 1; i <= iters; ++i) {
+            while (ld_flag<MODE>(mine) != (unsigned long long)i) { }
+            st_flag<MODE>(theirs, i);
+        }
+    }
+}
+
+// chain like the solver: every CTA, every phase: `nthreads` threads each store one 16 B LL message to both
+// neighbours, then poll their own two slots; __syncthreads between phases.  No compute.
+__device__ __forceinline__ void ll_store(uint4 *p, unsigned lo, unsigned hi, unsigned seq) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(seq), "r"(hi), "r"(seq) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__global__ void chain(uint4 *ll, int W, int phases, int active, int backoff, long long *cycles) {
+    const int cta = blockIdx.x, P = gridDim.x, t = threadIdx.x;
+    uint4 *up = cta > 0 ? ll + ((size_t)(cta - 1) * 2 + 1) * W : nullptr;
+    uint4 *dn = cta + 1 < P ? ll + ((size_t)(cta + 1) * 2) * W : nullptr;
+    const uint4 *it = ll + ((size_t)cta * 2) * W, *ib = ll + ((size_t)cta * 2 + 1) * W;
+    long long t0 = clock64();
+    for (int ph = 1; ph <= phases; ++ph) {
+        if (t < active) {
+            if (up) ll_store(up + t, ph, t, ph);
+            if (dn) ll_store(dn + t, ph, t, ph);
+            if (cta > 0) { uint4 r = ll_load(it + t); while (r.y < (unsigned)ph || r.w < (unsigned)ph) { if (backoff) __nanosleep(backoff); r = ll_load(it + t); } }
+            if (cta + 1 < P) { uint4 r = ll_load(ib + t); while (r.y < (unsigned)ph || r.w < (unsigned)ph) { if (backoff) __nanosleep(backoff); r = ll_load(ib + t); } }
+        }
+        __syncthreads();
+    }
+    if (t == 0 && cta == P / 2) *cycles = clock64() - t0;
+}
+
+// plain L2 load latency (pointer chase, one thread)
+__global__ void chase(const unsigned *next, int iters, long long *cycles, unsigned *sink) {
+    unsigned i = 0;
+    long long t0 = clock64();
+    for (int n = 0; n < iters; ++n) asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(i) : "l"(next + i) : "memory");
+    *cycles = clock64() - t0;
+    *sink = i;
+}
+
+int main() {
+    setvbuf(stdout, nullptr, _IONBF, 0);
+    unsigned long long *slots; long long *cyc;
+    CK(cudaMalloc(&slots, 32 * 8 * 256)); CK(cudaMallocManaged(&cyc, 8));
+    const int iters = 20000;
+    int peers[] = {1, 2, 37, 74, 147};
+    for (int mode = 0; mode < 3; ++mode)
+        for (int peer : peers) {
+            CK(cudaMemset(slots, 0, 32 * 8 * 256));
+            void *args[] = {&slots, (void *)&iters, &peer, &cyc};
+            void *fn = mode == 0 ? (void *)pingpong<0> : mode == 1 ? (void *)pingpong<1> : (void *)pingpong<2>;
+            CK(cudaLaunchCooperativeKernel(fn, dim3(148), dim3(32), args, 0, 0));
+            CK(cudaDeviceSynchronize());
+            printf("pingpong mode %d (0 volatile, 1 relaxed.gpu, 2 rel/acq.gpu) peer CTA %3d: %.0f cycles per one-way hop\n", mode, peer, (double)*cyc / iters / 2);
+        }
+    // pointer chase over 64 MB (L2 resident, > L1)
+    {
+        const int n = 1 << 24; unsigned *h = (unsigned *)malloc(n * 4), *d, *sink;
+        for (int i = 0; i < n; ++i) h[i] = (unsigned)(((long long)i * 40503 + 12345) % n);  // scattered
+        CK(cudaMalloc(&d, n * 4)); CK(cudaMalloc(&sink, 4)); CK(cudaMemcpy(d, h, n * 4, cudaMemcpyHostToDevice));
+        chase<<<1, 1>>>(d, 4000, cyc, sink); CK(cudaDeviceSynchronize());
+        chase<<<1, 1>>>(d, 4000, cyc, sink); CK(cudaDeviceSynchronize());
+        printf("dependent ld.volatile chase (64 MB footprint): %.0f cycles per load\n", (double)*cyc / 4000);
+    }
+    // solver-like chain
+    uint4 *ll; const int W = 1024;
+    CK(cudaMalloc(&ll, (size_t)148 * 2 * W * 16));
+    int actives[] = {1, 32, 128, 512};
+    int backs[] = {0, 100};
+    for (int b : backs)
+        for (int a : actives) {
+            CK(cudaMemset(ll, 0, (size_t)148 * 2 * W * 16));
+            int phases = 4000;
+            void *args[] = {&ll, (void *)&W, &phases, &a, &b, &cyc};
+            CK(cudaLaunchCooperativeKernel((void *)chain, dim3(148), dim3(512), args, 0, 0));
+            CK(cudaDeviceSynchronize());
+            printf("chain: 148 CTAs x %3d polling threads, backoff %3d ns: %.0f cycles per phase\n", a, b, (double)*cyc / phases);
+        }
+    return 0;
+}
