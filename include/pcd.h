@@ -145,6 +145,20 @@ int pcd_solver_set_check_lag(pcd_solver *s, int check_lag);
 int pcd_solver_run(pcd_solver *s, int max_iterations, double convergence_threshold, pcd_solve_info *info);
 int pcd_solver_path_used(const pcd_solver *s);
 
+/* ---- row-slab solver for multi-GPU runs (no counterpart in the reference) -------------------
+ * One process per GPU owns global rows [row0, row0+rows) of a width x height grid plus one ghost row above
+ * and below (local row r <-> global row row0+r-1).  The host layer (poisson_caustic_design_b200/slab.py,
+ * torch.distributed) exchanges the boundary rows between colour phases and all-reduces the per-sweep max.
+ * `cuda_stream` is the caller's stream (torch's current stream) so kernels and collectives order naturally. */
+typedef struct pcd_slab pcd_slab;
+int pcd_slab_create(int width, int height, int row0, int rows, int device, void *cuda_stream, pcd_slab **out);
+void pcd_slab_destroy(pcd_slab *s);
+int pcd_slab_device_ptrs(pcd_slab *s, void **phi_dev, void **D_dev, void **sweep_max_dev);
+int pcd_slab_upload(pcd_slab *s, const double *D_rows_with_ghosts, const double *phi_rows_with_ghosts);
+int pcd_slab_download(pcd_slab *s, double *phi_owned_rows);
+int pcd_slab_sweep_colour(pcd_slab *s, int colour, int slot);
+int pcd_slab_clear_max(pcd_slab *s, int n_slots);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,13 @@ ABI = [
     ("pcd_solver_set_check_lag", C.c_int, [C.c_void_p, C.c_int]),
     ("pcd_solver_run", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.POINTER(pcd_solve_info)]),
     ("pcd_solver_path_used", C.c_int, [C.c_void_p]),
+    ("pcd_slab_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("pcd_slab_destroy", None, [C.c_void_p]),
+    ("pcd_slab_device_ptrs", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    ("pcd_slab_upload", C.c_int, [C.c_void_p, _dp, _dp]),
+    ("pcd_slab_download", C.c_int, [C.c_void_p, _dp]),
+    ("pcd_slab_sweep_colour", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("pcd_slab_clear_max", C.c_int, [C.c_void_p, C.c_int]),
 ]
 
 

@@ -1,0 +1,86 @@
+"""CPU (gloo, world_size 2 and 3): the multi-GPU host logic of poisson_caustic_design_b200.slab -- row
+partition, one-row halo exchange per colour phase, all-reduced stopping rule -- with a numpy engine standing in
+for the CUDA slab.  The G-slab result must be bit-identical to the single-domain red-black oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _worker(rank, world, port, D, phi0, max_it, tol, check_every, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from poisson_caustic_design_b200 import slab
+    from slab_numpy_engine import NumpySlabEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    H, W = D.shape
+    row0, rows = slab.partition(H, world, rank)
+    eng = NumpySlabEngine(W, H, row0, rows)
+    eng.upload(slab.with_ghosts(D, row0, rows), slab.with_ghosts(phi0, row0, rows))
+    info = slab.solve(eng, dist, rank, world, max_it, tol, check_every)
+    np.save(os.path.join(out_dir, f"phi_{rank}.npy"), eng.download())
+    np.save(os.path.join(out_dir, f"info_{rank}.npy"), np.array([info["sweeps"], info["converged_at"], info["last_max_update"]]))
+    dist.destroy_process_group()
+
+
+def run_world(world, D, phi0, max_it, tol, check_every, tmp_path, port):
+    mp.spawn(_worker, args=(world, port, D, phi0, max_it, tol, check_every, str(tmp_path)), nprocs=world, join=True)
+    phi = np.concatenate([np.load(tmp_path / f"phi_{r}.npy") for r in range(world)], axis=0)
+    infos = [np.load(tmp_path / f"info_{r}.npy") for r in range(world)]
+    for i in infos[1:]:
+        assert np.array_equal(i, infos[0])           # every rank took the same decision
+    return phi, infos[0]
+
+
+def test_partition_covers_the_grid():
+    from poisson_caustic_design_b200 import slab
+    for H in (1, 7, 64, 1000, 8192):
+        for world in (1, 2, 3, 8):
+            parts = [slab.partition(H, world, r) for r in range(world)]
+            assert parts[0][0] == 0 and sum(p[1] for p in parts) == H
+            for a, b in zip(parts, parts[1:]):
+                assert a[0] + a[1] == b[0]
+            assert max(p[1] for p in parts) - min(p[1] for p in parts) <= 1
+    g = slab.with_ghosts(np.arange(12.0).reshape(4, 3), 0, 2)
+    assert g.shape == (4, 3) and not g[0].any() and np.array_equal(g[1:], np.arange(9.0).reshape(3, 3))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_slabs_bit_identical_to_single_domain(port, world, tmp_path):
+    rng = np.random.RandomState(world)
+    H, W = 37, 26                                     # uneven partition
+    D = rng.standard_normal((H, W))
+    D[10:13, 5:9] = np.nan                            # a hole straddling slab interiors
+    D[18, 20] = np.nan
+    D[np.isfinite(D)] -= D[np.isfinite(D)].mean()
+    phi0 = rng.standard_normal((H, W))
+    phi, info = run_world(world, D, phi0, 25, 0.0, 8, tmp_path, 29600 + world)
+    want, n, conv, last = port.poisson_rb(D, phi0, 25, 0.0)
+    assert int(info[0]) == 25 and int(info[1]) == 0
+    assert np.array_equal(phi, want, equal_nan=True)
+    assert info[2] == last
+
+
+def test_gloo_slabs_stopping_rule(port, tmp_path):
+    rng = np.random.RandomState(9)
+    H, W = 24, 32
+    D = rng.standard_normal((H, W))
+    D -= D.mean()
+    z = np.zeros_like(D)
+    phi, info = run_world(2, D, z, 100000, 1e-7, 16, tmp_path, 29650)
+    _, n_exact, conv_exact, _ = port.poisson_rb(D, z, 100000, 1e-7)
+    assert int(info[1]) == conv_exact                 # same sweep satisfies max|delta| < tol
+    assert int(info[0]) % 16 == 0 and 0 <= int(info[0]) - conv_exact < 16
+    want = port.poisson_rb(D, z, 100000, 1e-7, extra_sweeps=int(info[0]) - conv_exact)[0]
+    assert np.array_equal(phi, want)
+    assert info[2] < 1e-7
