@@ -64,9 +64,10 @@ typedef enum pcd_field {
 
 /* Which SOR kernel family runs a solve. */
 typedef enum pcd_solver_path {
-    PCD_SOLVER_AUTO = 0,       /* resident when the grid fits on chip, streaming otherwise */
-    PCD_SOLVER_STREAMING = 1,  /* one launch per colour, phi/D streamed from HBM/L2 */
-    PCD_SOLVER_RESIDENT = 2    /* one persistent cooperative kernel, phi/D tiles live in shared memory */
+    PCD_SOLVER_AUTO = 0,       /* resident when the grid fits on chip, tiled otherwise */
+    PCD_SOLVER_STREAMING = 1,  /* one launch per colour, phi/D streamed from HBM/L2 (also the NaN-hole path) */
+    PCD_SOLVER_RESIDENT = 2,   /* one persistent cooperative kernel, phi/D live in registers/shared memory */
+    PCD_SOLVER_TILED = 3       /* temporal blocking: several sweeps per pass over shared-memory tiles, ping-pong fields */
 } pcd_solver_path;
 
 typedef struct pcd_config {

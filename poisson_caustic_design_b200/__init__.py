@@ -20,8 +20,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libpcd_b200.so")
 
 PCD_OK, PCD_ERR_INVALID, PCD_ERR_CUDA, PCD_ERR_NO_DEVICE, PCD_ERR_RASTER_MISS, PCD_ERR_STATE, PCD_ERR_UNSUPPORTED = range(7)
-SOLVER_AUTO, SOLVER_STREAMING, SOLVER_RESIDENT = 0, 1, 2
-SOLVER_PATH_NAMES = {SOLVER_AUTO: "auto", SOLVER_STREAMING: "streaming", SOLVER_RESIDENT: "resident"}
+SOLVER_AUTO, SOLVER_STREAMING, SOLVER_RESIDENT, SOLVER_TILED = 0, 1, 2, 3
+SOLVER_PATH_NAMES = {SOLVER_AUTO: "auto", SOLVER_STREAMING: "streaming", SOLVER_RESIDENT: "resident", SOLVER_TILED: "tiled"}
 
 FIELDS = {
     "phi": 0, "h": 1, "raster": 2, "pixels": 3, "divergence": 4, "norm_x": 5, "norm_y": 6,

@@ -42,4 +42,10 @@ struct ResState {  // device control block of the resident kernel (mirrored in p
 int resident_plan(pcd_solver *s);   // 1 when the grid fits the on-chip path (fills s->res_*)
 int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double tol, pcd_solve_info *info);
 
+
+// sor_tiled.cu
+int tiled_sweeps_per_pass();
+int tiled_pass(const double *phi_in, double *phi_out, const double *D, int W, int H, int row_first, int rows, int grow0,
+               int nsweeps, unsigned long long *slots, cudaStream_t stream);
+
 }  // namespace pcd

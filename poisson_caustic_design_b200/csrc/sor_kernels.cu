@@ -131,6 +131,54 @@ static int run_streaming(pcd_solver *s, const double *D, double *phi, int max_it
     return PCD_OK;
 }
 
+// Tiled path (sor_tiled.cu): TS sweeps per pass, ping-pong between phi and a second buffer.
+static int run_tiled(pcd_solver *s, const double *D, double *phi, int max_it, double tol, pcd_solve_info *info) {
+    const int W = s->W, H = s->H;
+    const int TS = tiled_sweeps_per_pass();
+    if (!s->phi_alt) PCD_CUDA(cudaMalloc(&s->phi_alt, sizeof(double) * (size_t)W * H));
+    int chunk = s->check_lag > 0 ? s->check_lag : 64;
+    chunk = ((chunk + TS - 1) / TS) * TS;  // whole passes
+    if (chunk > 4096) chunk = 4096;
+    double *cur = phi, *alt = s->phi_alt;
+    int done = 0, conv = 0;
+    double last = 0.0;
+    while (done < max_it && !conv) {
+        const int k = max_it - done < chunk ? max_it - done : chunk;
+        PCD_CUDA(cudaMemsetAsync(s->sweep_max, 0, sizeof(unsigned long long) * k, s->stream));
+        PCD_CUDA(cudaEventRecord(s->evk0, s->stream));
+        for (int j = 0; j < k;) {
+            const int ns = k - j < TS ? k - j : TS;
+            PCD_TRY(tiled_pass(cur, alt, D, W, H, 0, H, 0, ns, s->sweep_max + j, s->stream));
+            info->launches++;
+            double *t = cur; cur = alt; alt = t;
+            j += ns;
+        }
+        PCD_CUDA(cudaEventRecord(s->evk1, s->stream));
+        PCD_CUDA(cudaMemcpyAsync(s->h_sweep_max, s->sweep_max, sizeof(unsigned long long) * k, cudaMemcpyDeviceToHost, s->stream));
+        PCD_CUDA(cudaStreamSynchronize(s->stream));
+        {
+            float kms = 0.f;
+            PCD_CUDA(cudaEventElapsedTime(&kms, s->evk0, s->evk1));
+            info->kernel_ms += kms;
+        }
+        for (int j = 0; j < k; ++j) {
+            double m;
+            memcpy(&m, &s->h_sweep_max[j], sizeof(double));
+            if (!conv && m < tol) {
+                conv = done + j + 1;
+                last = m;
+            }
+            if (!conv && j == k - 1) last = m;
+        }
+        done += k;
+    }
+    if (cur != phi) PCD_CUDA(cudaMemcpyAsync(phi, cur, sizeof(double) * (size_t)W * H, cudaMemcpyDeviceToDevice, s->stream));
+    info->sweeps = done;
+    info->converged_at = conv;
+    info->last_max_update = last;
+    return PCD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // solver object
 // ------------------------------------------------------------------------------------------------
@@ -162,8 +210,9 @@ int solver_init(pcd_solver *s, int W, int H, int device, int path, cudaStream_t 
     PCD_CUDA(cudaEventCreate(&s->ev1));
     PCD_CUDA(cudaEventCreate(&s->evk0));
     PCD_CUDA(cudaEventCreate(&s->evk1));
-    s->path_used = PCD_SOLVER_STREAMING;
-    if (path != PCD_SOLVER_STREAMING) {
+    // AUTO: resident when the grid fits on chip, else tiled (temporal blocking); STREAMING = plain colour launches
+    s->path_used = (path == PCD_SOLVER_STREAMING) ? PCD_SOLVER_STREAMING : PCD_SOLVER_TILED;
+    if (path == PCD_SOLVER_AUTO || path == PCD_SOLVER_RESIDENT) {
         int coop = 0;
         PCD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
         if (coop && resident_plan(s)) {
@@ -181,7 +230,7 @@ void solver_free(pcd_solver *s) {
     if (!s) return;
     cudaFree(s->sweep_max); cudaFreeHost(s->h_sweep_max);
     cudaFree(s->mask); cudaFree(s->d_flags); cudaFreeHost(s->h_flags);
-    cudaFree(s->res_state); cudaFreeHost(s->h_res_state); cudaFree(s->halo);
+    cudaFree(s->res_state); cudaFreeHost(s->h_res_state); cudaFree(s->halo); cudaFree(s->phi_alt);
     if (s->own_fields) { cudaFree(s->D); cudaFree(s->phi); }
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -218,7 +267,13 @@ int solver_run(pcd_solver *s, const double *D, double *phi, int max_iterations, 
             PCD_LAUNCHED();
             info->launches++;
         }
-        rc = run_streaming(s, D, phi, max_iterations, tol, masked, info);
+        // the tiled path derives neighbour counts from coordinates: NaN holes go through the masked colour kernels
+        if (s->path_used == PCD_SOLVER_TILED && !masked) {
+            rc = run_tiled(s, D, phi, max_iterations, tol, info);
+        } else {
+            info->path = PCD_SOLVER_STREAMING;
+            rc = run_streaming(s, D, phi, max_iterations, tol, masked, info);
+        }
     }
     PCD_TRY(rc);
     PCD_CUDA(cudaEventRecord(s->ev1, s->stream));

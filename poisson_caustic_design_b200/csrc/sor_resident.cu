@@ -72,23 +72,19 @@ struct Strip {
     unsigned valid;            // bit 2j+q
 };
 
-// Update of the active cell of row J in a colour phase.  P0 = column parity of the active cell of row 0;
-// row j's active cell has parity (P0+j)&1.
+// Arithmetic of the update of the active cell of row J in a colour phase (no shared-memory traffic: `nb` was read
+// before, the new value is stored afterwards, so the NR independent dependency chains of a phase overlap).
+// P0 = column parity of the active cell of row 0; row j's active cell has parity (P0+j)&1.
 template <int NR, int P0, bool FAST, bool EDGE, int J>
-__device__ __forceinline__ void res_cell(Strip<NR> &s, double *__restrict__ smk, const int /*Kp*/, const double hu,
-                                         const double hd, const ResParams &p, double &lmax, const int k,
-                                         uint4 *ll_up, uint4 *ll_dn, const unsigned seq) {
+__device__ __forceinline__ bool res_cell(Strip<NR> &s, const double nb, const double hu, const double hd,
+                                         const ResParams &p, double &lmax) {
     constexpr int j = J;
     constexpr int q = (P0 + j) & 1;
-    constexpr int Kp = RES_KP;
-    // the one neighbour owned by another thread: left (q = 0) or right (q = 1), other parity row in smem
-    const double nb = (q == 0) ? smk[(j * 2 + 1) * Kp - 1] : smk[(j * 2 + 0) * Kp + 1];
     const double own = s.v[j][q ^ 1];
     const double l = (q == 0) ? nb : own, r = (q == 0) ? own : nb;
     const double u = (j == 0) ? hu : s.v[(j == 0) ? 0 : j - 1][q];
     const double d = (j == NR - 1) ? hd : s.v[(j == NR - 1) ? j : j + 1][q];
     const double val = s.v[j][q];
-    double nv;
     if (FAST) {
         // only the first / last slab (EDGE) has rows whose neighbour count differs from the interior rows'
         const double cnt = (EDGE && j == 0) ? s.cT[q] : ((EDGE && j == NR - 1) ? s.cB[q] : s.cM[q]);
@@ -97,9 +93,10 @@ __device__ __forceinline__ void res_cell(Strip<NR> &s, double *__restrict__ smk,
         const double delta = wv * ((sum - cnt * val) - s.D[j][q]);
         const double ad = fabs(delta);
         if (ad > lmax) lmax = ad;
-        nv = val + delta;
+        s.v[j][q] = val + delta;
+        return true;
     } else {
-        if (!((s.valid >> (2 * j + q)) & 1u)) return;
+        if (!((s.valid >> (2 * j + q)) & 1u)) return false;
         const unsigned mm = (unsigned)(s.masks >> (8 * j + 4 * q)) & 15u;
         double sum = 0.0;
         if (mm & 1) sum += l;
@@ -110,30 +107,48 @@ __device__ __forceinline__ void res_cell(Strip<NR> &s, double *__restrict__ smk,
         const double delta = wsel(p.w, cnt) * (sum - (double)cnt * val - s.D[j][q]);
         const double ad = fabs(delta);
         if (ad > lmax) lmax = ad;
-        nv = val + delta;
+        s.v[j][q] = val + delta;
+        return true;
     }
-    s.v[j][q] = nv;
-    smk[(j * 2 + q) * Kp] = nv;
-    if (j == 0 && ll_up) ll_store(ll_up + 2 * k + q, nv, seq);
-    if (j == NR - 1 && ll_dn) ll_store(ll_dn + 2 * k + q, nv, seq);
+}
+
+template <int NR, int P0, int J>
+__device__ __forceinline__ double res_nb(const double *__restrict__ smk) {
+    constexpr int q = (P0 + J) & 1, Kp = RES_KP;
+    // the one neighbour owned by another thread: left (q = 0) or right (q = 1), other parity row in smem
+    return (q == 0) ? smk[(J * 2 + 1) * Kp - 1] : smk[(J * 2 + 0) * Kp + 1];
 }
 
 template <int NR, int P0, bool FAST, bool EDGE, int J>
 struct InteriorRows {  // rows J .. NR-2 (compile-time recursion keeps every register index static)
-    static __device__ __forceinline__ void run(Strip<NR> &s, double *__restrict__ smk, const int Kp, const ResParams &p,
-                                               double &lmax, const int k, const unsigned seq) {
+    static __device__ __forceinline__ void load(const double *__restrict__ smk, double (&nb)[NR]) {
         if constexpr (J <= NR - 2) {
-            res_cell<NR, P0, FAST, EDGE, J>(s, smk, Kp, 0.0, 0.0, p, lmax, k, nullptr, nullptr, seq);
-            InteriorRows<NR, P0, FAST, EDGE, J + 1>::run(s, smk, Kp, p, lmax, k, seq);
+            nb[J] = res_nb<NR, P0, J>(smk);
+            InteriorRows<NR, P0, FAST, EDGE, J + 1>::load(smk, nb);
+        }
+    }
+    static __device__ __forceinline__ void compute(Strip<NR> &s, const double (&nb)[NR], bool (&ok)[NR], const ResParams &p,
+                                                   double &lmax) {
+        if constexpr (J <= NR - 2) {
+            ok[J] = res_cell<NR, P0, FAST, EDGE, J>(s, nb[J], 0.0, 0.0, p, lmax);
+            InteriorRows<NR, P0, FAST, EDGE, J + 1>::compute(s, nb, ok, p, lmax);
+        }
+    }
+    static __device__ __forceinline__ void store(const Strip<NR> &s, double *__restrict__ smk, const bool (&ok)[NR]) {
+        if constexpr (J <= NR - 2) {
+            constexpr int q = (P0 + J) & 1;
+            if (ok[J]) smk[(J * 2 + q) * RES_KP] = s.v[J][q];
+            InteriorRows<NR, P0, FAST, EDGE, J + 1>::store(s, smk, ok);
         }
     }
 };
 
 // One colour phase of one slab: interior rows first (they need nothing from other CTAs), then the halo
 // messages of the previous phase are consumed and the two boundary rows are updated and exported -- so a
-// message is in flight while both CTAs work on their interiors.
+// message is in flight while both CTAs work on their interiors.  Within each group all shared-memory reads come
+// first, then the arithmetic, then the writes.
 template <int NR, int P0, bool FAST, bool EDGE>
-__device__ __forceinline__ void res_phase(Strip<NR> &s, double *__restrict__ smk, const int Kp, double &hu, double &hd,
+__device__ __forceinline__ void res_phase(Strip<NR> &s, double *__restrict__ smk, const int /*Kp*/, double &hu, double &hd,
                                           const ResParams &p, double &lmax, const int k, uint4 *ll_up, uint4 *ll_dn,
                                           const unsigned seq, const uint4 *in_t, const uint4 *in_b, const bool first) {
     uint4 rt = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
@@ -141,13 +156,32 @@ __device__ __forceinline__ void res_phase(Strip<NR> &s, double *__restrict__ smk
         if (in_t) rt = ll_issue(in_t);
         if (in_b) rb = ll_issue(in_b);
     }
-    InteriorRows<NR, P0, FAST, EDGE, 1>::run(s, smk, Kp, p, lmax, k, seq);
+    double nb[NR];
+    bool ok[NR];
+    nb[0] = res_nb<NR, P0, 0>(smk);
+    if constexpr (NR >= 2) nb[NR - 1] = res_nb<NR, P0, NR - 1>(smk);
+    InteriorRows<NR, P0, FAST, EDGE, 1>::load(smk, nb);
+    InteriorRows<NR, P0, FAST, EDGE, 1>::compute(s, nb, ok, p, lmax);
+    InteriorRows<NR, P0, FAST, EDGE, 1>::store(s, smk, ok);
     if (!first) {
         if (in_t) hu = ll_consume(rt, in_t, seq - 1u);
         if (in_b) hd = ll_consume(rb, in_b, seq - 1u);
     }
-    res_cell<NR, P0, FAST, EDGE, 0>(s, smk, Kp, hu, hd, p, lmax, k, ll_up, ll_dn, seq);
-    if constexpr (NR >= 2) res_cell<NR, P0, FAST, EDGE, NR - 1>(s, smk, Kp, hu, hd, p, lmax, k, ll_up, ll_dn, seq);
+    constexpr int q0 = P0 & 1, qb = (P0 + NR - 1) & 1;
+    const bool ok0 = res_cell<NR, P0, FAST, EDGE, 0>(s, nb[0], hu, hd, p, lmax);
+    bool okb = false;
+    if constexpr (NR >= 2) okb = res_cell<NR, P0, FAST, EDGE, NR - 1>(s, nb[NR - 1], hu, hd, p, lmax);
+    if (ok0) {
+        smk[(0 * 2 + q0) * RES_KP] = s.v[0][q0];
+        if (ll_up) ll_store(ll_up + 2 * k + q0, s.v[0][q0], seq);
+        if (NR == 1 && ll_dn) ll_store(ll_dn + 2 * k + q0, s.v[0][q0], seq);
+    }
+    if constexpr (NR >= 2) {
+        if (okb) {
+            smk[((NR - 1) * 2 + qb) * RES_KP] = s.v[NR - 1][qb];
+            if (ll_dn) ll_store(ll_dn + 2 * k + qb, s.v[NR - 1][qb], seq);
+        }
+    }
 }
 
 template <int NR, bool EDGE>

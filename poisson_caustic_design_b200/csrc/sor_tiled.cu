@@ -1,0 +1,293 @@
+// K-SOR, wavefront streaming path for grids that do not fit on chip (C5: 8192 x 8192): temporal blocking by
+// time-skewed row streaming.
+//
+// One pass advances the field by TS full red-black sweeps (NP = 2*TS colour phases) while phi and D cross HBM
+// once in and phi once out (ping-pong fields).  A CTA owns a strip of 2*NT columns (minus a 2*TS-column skirt
+// on each side that goes stale by one column per phase and is never written) and a chunk of rows, and walks
+// DOWN the rows: at step f, phase p updates row f - 1 - 2p.  With a skew of two rows per phase every phase of a
+// step only reads values produced in earlier steps (phase p at row r needs phase p-1 at rows r-1..r+1, done at
+// step f-1 at the latest), so the whole step needs ONE barrier and updates are in place.  Thread k owns the
+// column pair (2k, 2k+1): its rolling window of R rows lives in registers (ring indices AND the colour parity
+// of every update are compile-time: the row loop is unrolled by the even period R and chunks start on a fixed
+// parity), so up/down/own values are register reads; the single left/right neighbour owned by thread k-1/k+1
+// goes through a shared-memory ring that also receives the rows streamed in by cp.async PF steps ahead (no
+// staging registers, no extra barrier).  Blocks of R steps that lie entirely inside the chunk and away from the
+// domain's top/bottom rows run a check-free variant.  The chunk starts NP rows early and ends NP rows late
+// (staleness advances one row per phase, so owned rows stay exact); per-sweep maxima are taken over owned cells
+// only.  Every owned value equals the global red-black iteration bit for bit.
+//
+// Neighbour rule / update / max: src/solver.cpp:29-56 (no NaN holes on this path: the solver falls back to the
+// masked colour kernels when D contains NaN).
+#include <cuda_pipeline_primitives.h>
+
+#include "sor_common.cuh"
+
+namespace pcd {
+
+constexpr int WAVE_NT = 256;  // threads = column pairs per strip window
+constexpr int WAVE_PF = 4;    // rows prefetched ahead by cp.async
+
+template <int TS>
+struct WaveCfg {
+    static constexpr int NP = 2 * TS;                            // colour phases per pass
+    static constexpr int R = ((2 * NP + WAVE_PF + 1) + 1) & ~1;  // ring period (rows), even
+    static constexpr int HX = 2 * TS;                            // stale skirt columns on each side of the window
+    static constexpr int LXW = 2 * WAVE_NT;                      // window columns
+    static constexpr int CORE = LXW - 2 * HX;                    // columns written by the strip
+    static constexpr int PITCH = WAVE_NT + 2;                    // smem pitch of one parity row (pad on each side)
+};
+
+struct WaveParams {
+    const double *phi_in;
+    double *phi_out;
+    const double *D;
+    int W, H;            // global grid
+    int row_first, rows; // owned global rows [row_first, row_first + rows)
+    int grow0;           // global row of local row 0 of the arrays
+    int chunk_rows;
+    SorW w;
+    unsigned long long *slots;  // per-sweep max, TS entries used
+};
+
+struct WaveThread {  // per-thread invariants
+    int k, gx0;
+    bool ex0, ex1, core;
+    double cx[2], wx[2];
+    int ys, ye, y0, y1;
+};
+
+// One row step.  C = (f - ys) mod R is compile-time; chunks start so that the active cell of row r in phase ph
+// has window parity (r - ys + 1 + ph) & 1, i.e. (C + ph) & 1 for the row f-1-2ph updated at offset C.
+template <int TS, int C, bool STEADY>
+__device__ __forceinline__ void wave_step(const WaveParams &p, const WaveThread &t, const int f,
+                                          double (&v)[WaveCfg<TS>::R][2], double *__restrict__ sphi,
+                                          double *__restrict__ sD, double (&lmax)[TS]) {
+    using Cfg = WaveCfg<TS>;
+    constexpr int R = Cfg::R, NP = Cfg::NP, PITCH = Cfg::PITCH;
+    const int W = p.W, H = p.H, k = t.k;
+    // (a) stream row f+PF into ring slot (C+PF)%R: 8-byte cp.async per cell, zero-filled outside the grid
+    {
+        constexpr int SL = (C + WAVE_PF) % R;
+        const int fr = f + WAVE_PF;
+        const bool row_ok = STEADY ? true : (fr <= t.ye && fr >= 0 && fr < H);
+        const size_t base = row_ok ? (size_t)(fr - p.grow0) * W : 0;
+        const bool a0 = row_ok && t.ex0, a1 = row_ok && t.ex1;
+        const size_t o0 = a0 ? base + t.gx0 : 0, o1 = a1 ? base + t.gx0 + 1 : 0;
+        __pipeline_memcpy_async(sphi + (SL * 2 + 0) * PITCH + 1 + k, p.phi_in + o0, 8, a0 ? 0 : 8);
+        __pipeline_memcpy_async(sphi + (SL * 2 + 1) * PITCH + 1 + k, p.phi_in + o1, 8, a1 ? 0 : 8);
+        __pipeline_memcpy_async(sD + (SL * 2 + 0) * PITCH + 1 + k, p.D + o0, 8, a0 ? 0 : 8);
+        __pipeline_memcpy_async(sD + (SL * 2 + 1) * PITCH + 1 + k, p.D + o1, 8, a1 ? 0 : 8);
+        __pipeline_commit();
+    }
+    // (b) row f becomes active: own pair from the smem ring into the register ring
+    v[C][0] = sphi[(C * 2 + 0) * PITCH + 1 + k];
+    v[C][1] = sphi[(C * 2 + 1) * PITCH + 1 + k];
+    // (c) phases: phase ph updates row f - 1 - 2*ph (row f, just activated, is phase 0's lower neighbour).
+    // The NP updates of a step are independent of each other: all shared-memory reads are issued first, then
+    // the arithmetic, then all writes, so the NP dependency chains overlap instead of being serialised by the
+    // (possible-alias) ordering of smem stores and loads.
+    double nbv[NP], Dvv[NP], nvv[NP];
+    bool act[NP];
+#pragma unroll
+    for (int ph = 0; ph < NP; ++ph) {
+        const int SL = (C - 1 - 2 * ph + 2 * R) % R;
+        const int q = (C + ph) & 1;  // compile-time after unrolling
+        const int r = f - 1 - 2 * ph;
+        // rows that still matter for the owned rows: the dependency pyramid shrinks by one row per phase
+        bool a = q ? t.ex1 : t.ex0;
+        if (!STEADY) a = a && !(r < t.y0 - (NP - 1 - ph) || r > t.y1 - 1 + (NP - 1 - ph) || r < 0 || r >= H);
+        act[ph] = a;
+        nbv[ph] = q ? sphi[(SL * 2 + 0) * PITCH + 1 + k + 1] : sphi[(SL * 2 + 1) * PITCH + 1 + k - 1];
+        Dvv[ph] = sD[(SL * 2 + q) * PITCH + 1 + k];
+    }
+#pragma unroll
+    for (int ph = 0; ph < NP; ++ph) {
+        const int SL = (C - 1 - 2 * ph + 2 * R) % R, SU = (SL + R - 1) % R, SD = (SL + 1) % R;
+        const int q = (C + ph) & 1;
+        const int r = f - 1 - 2 * ph;
+        const double own = v[SL][q ^ 1];
+        const double l = q ? own : nbv[ph], rr = q ? nbv[ph] : own;
+        const double u = v[SU][q], d = v[SD][q];
+        const double val = v[SL][q];
+        const double sum = ((l + u) + rr) + d;  // ghost rows / columns read 0.0: identical to skipping them
+        double delta;
+        if (!STEADY && (r == 0 || r == H - 1)) {  // CTA-uniform: domain top / bottom row
+            const int cnt = (int)t.cx[q] - (r == 0 ? 1 : 0) - (r == H - 1 ? 1 : 0);
+            delta = wsel(p.w, cnt) * ((sum - (double)cnt * val) - Dvv[ph]);
+        } else {
+            delta = t.wx[q] * ((sum - t.cx[q] * val) - Dvv[ph]);
+        }
+        const double nv = act[ph] ? val + delta : val;
+        nvv[ph] = nv;
+        v[SL][q] = nv;
+        if (act[ph] && t.core && (STEADY || (r >= t.y0 && r < t.y1))) {
+            const double ad = fabs(delta);
+            if (ad > lmax[ph / 2]) lmax[ph / 2] = ad;
+        }
+    }
+#pragma unroll
+    for (int ph = 0; ph < NP; ++ph) {
+        const int SL = (C - 1 - 2 * ph + 2 * R) % R;
+        const int q = (C + ph) & 1;
+        if (act[ph]) sphi[(SL * 2 + q) * PITCH + 1 + k] = nvv[ph];
+    }
+    // (d) the row that just finished its last phase leaves through the output field
+    {
+        constexpr int SL = (C - 1 - 2 * (NP - 1) + 2 * R) % R;
+        const int r = f - 1 - 2 * (NP - 1);
+        if (t.core && (STEADY || (r >= t.y0 && r < t.y1))) {
+            const size_t o = (size_t)(r - p.grow0) * W + t.gx0;
+            if (t.ex0 && t.ex1 && ((W & 1) == 0)) {
+                *reinterpret_cast<double2 *>(p.phi_out + o) = make_double2(v[SL][0], v[SL][1]);
+            } else {
+                if (t.ex0) p.phi_out[o] = v[SL][0];
+                if (t.ex1) p.phi_out[o + 1] = v[SL][1];
+            }
+        }
+    }
+    // (e) row f+1 must have landed before the next step reads it
+    __pipeline_wait_prior(WAVE_PF - 1);
+    __syncthreads();
+}
+
+template <int TS, int C, bool STEADY>
+struct WaveUnroll {
+    static __device__ __forceinline__ void run(const WaveParams &p, const WaveThread &t, const int f,
+                                               double (&v)[WaveCfg<TS>::R][2], double *sphi, double *sD, double (&lmax)[TS]) {
+        wave_step<TS, C, STEADY>(p, t, f + C, v, sphi, sD, lmax);
+        if constexpr (C + 1 < WaveCfg<TS>::R) WaveUnroll<TS, C + 1, STEADY>::run(p, t, f, v, sphi, sD, lmax);
+    }
+};
+
+template <int TS>
+__global__ void __launch_bounds__(WAVE_NT, 2) sor_wave_kernel(const __grid_constant__ WaveParams p) {
+    using Cfg = WaveCfg<TS>;
+    constexpr int R = Cfg::R, NP = Cfg::NP, PITCH = Cfg::PITCH;
+    extern __shared__ double smem[];
+    double *sphi = smem;                   // [R][2][PITCH]
+    double *sD = smem + R * 2 * PITCH;     // [R][2][PITCH]
+    __shared__ double wred[TS][WAVE_NT / 32];
+
+    WaveThread t;
+    t.k = threadIdx.x;
+    const int W = p.W, H = p.H;
+    const int xw0 = blockIdx.x * Cfg::CORE - Cfg::HX;              // window origin (global x, even)
+    t.y0 = p.row_first + blockIdx.y * p.chunk_rows;
+    t.y1 = min(t.y0 + p.chunk_rows, p.row_first + p.rows);
+    if (t.y0 >= t.y1) return;
+    // first row streamed in: NP rows of warm-up, moved one row earlier when needed so that the colour parity of
+    // every (step offset, phase) pair is a compile-time constant: active parity of row r in phase ph is
+    // (xw0 + r + ph) & 1 = (r + ph) & 1, and r = ys + C - 1 - 2ph at offset C  =>  need ys odd
+    t.ys = t.y0 - NP;
+    if ((t.ys & 1) == 0) t.ys -= 1;
+    t.ye = t.y1 - 1 + NP;                                           // last row streamed in
+    t.gx0 = xw0 + 2 * t.k;
+    t.ex0 = t.gx0 >= 0 && t.gx0 < W;
+    t.ex1 = t.gx0 + 1 >= 0 && t.gx0 + 1 < W;
+    t.core = (2 * t.k >= Cfg::HX) && (2 * t.k < Cfg::LXW - Cfg::HX);
+    {
+        const int c0 = 4 - (t.gx0 == 0 ? 1 : 0) - (t.gx0 == W - 1 ? 1 : 0), c1 = 4 - (t.gx0 + 1 == 0 ? 1 : 0) - (t.gx0 + 1 == W - 1 ? 1 : 0);
+        t.cx[0] = (double)c0; t.cx[1] = (double)c1;
+        t.wx[0] = wsel(p.w, c0); t.wx[1] = wsel(p.w, c1);
+    }
+    for (int i = t.k; i < 2 * R * 2 * PITCH; i += WAVE_NT) smem[i] = 0.0;
+    __syncthreads();
+
+    double v[R][2];
+#pragma unroll
+    for (int i = 0; i < R; ++i) { v[i][0] = 0.0; v[i][1] = 0.0; }
+    double lmax[TS];
+#pragma unroll
+    for (int s = 0; s < TS; ++s) lmax[s] = 0.0;
+
+    // prologue: rows ys .. ys+PF-1 (slots 0..PF-1)
+#pragma unroll
+    for (int j = 0; j < WAVE_PF; ++j) {
+        const int fr = t.ys + j;
+        const bool row_ok = fr <= t.ye && fr >= 0 && fr < H;
+        const size_t base = row_ok ? (size_t)(fr - p.grow0) * W : 0;
+        const bool a0 = row_ok && t.ex0, a1 = row_ok && t.ex1;
+        const size_t o0 = a0 ? base + t.gx0 : 0, o1 = a1 ? base + t.gx0 + 1 : 0;
+        __pipeline_memcpy_async(sphi + (j * 2 + 0) * PITCH + 1 + t.k, p.phi_in + o0, 8, a0 ? 0 : 8);
+        __pipeline_memcpy_async(sphi + (j * 2 + 1) * PITCH + 1 + t.k, p.phi_in + o1, 8, a1 ? 0 : 8);
+        __pipeline_memcpy_async(sD + (j * 2 + 0) * PITCH + 1 + t.k, p.D + o0, 8, a0 ? 0 : 8);
+        __pipeline_memcpy_async(sD + (j * 2 + 1) * PITCH + 1 + t.k, p.D + o1, 8, a1 ? 0 : 8);
+        __pipeline_commit();
+    }
+    __pipeline_wait_prior(WAVE_PF - 1);
+    __syncthreads();
+
+    const int f_last = t.y1 + 2 * (NP - 1);
+    for (int fb = t.ys; fb <= f_last; fb += R) {
+        // a block of R steps is steady when every row any phase touches is owned and not a domain edge row, and
+        // every row streamed in exists
+        const int r_min = fb - 1 - 2 * (NP - 1), r_max = fb + R - 2, f_max = fb + R - 1 + WAVE_PF;
+        const bool steady = r_min >= max(t.y0, 1) && r_max <= min(t.y1 - 1, H - 2) && f_max <= min(t.ye, H - 1);
+        if (steady) WaveUnroll<TS, 0, true>::run(p, t, fb, v, sphi, sD, lmax);
+        else WaveUnroll<TS, 0, false>::run(p, t, fb, v, sphi, sD, lmax);
+    }
+
+    // publish the per-sweep maxima
+    __pipeline_wait_prior(0);
+#pragma unroll
+    for (int s = 0; s < TS; ++s) {
+        const double m = warp_max(lmax[s]);
+        if ((t.k & 31) == 0) wred[s][t.k >> 5] = m;
+    }
+    __syncthreads();
+    if (t.k < 32) {
+#pragma unroll
+        for (int s = 0; s < TS; ++s) {
+            double m = t.k < WAVE_NT / 32 ? wred[s][t.k] : 0.0;
+            m = warp_max(m);
+            if (t.k == 0 && m > 0.0) atomicMax(p.slots + s, (unsigned long long)__double_as_longlong(m));
+        }
+    }
+}
+
+constexpr int TILED_TS = 2;
+int tiled_sweeps_per_pass() { return TILED_TS; }
+
+template <int TS>
+static int launch_wave(const WaveParams &prm, int sm_count, cudaStream_t stream) {
+    using Cfg = WaveCfg<TS>;
+    static bool attr_set = false;
+    const size_t smem = (size_t)2 * Cfg::R * 2 * Cfg::PITCH * sizeof(double);
+    if (!attr_set) {
+        PCD_CUDA(cudaFuncSetAttribute(sor_wave_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    WaveParams p = prm;
+    const int strips = (p.W + Cfg::CORE - 1) / Cfg::CORE;
+    // about two CTAs per SM; chunks long enough that the 2*NP warm-up rows stay a small fraction
+    int chunks = (2 * sm_count + strips - 1) / strips;
+    const int min_rows = 16 * Cfg::NP;
+    if (chunks * min_rows > p.rows) chunks = p.rows / min_rows;
+    if (chunks < 1) chunks = 1;
+    p.chunk_rows = (p.rows + chunks - 1) / chunks;
+    chunks = (p.rows + p.chunk_rows - 1) / p.chunk_rows;
+    sor_wave_kernel<TS><<<dim3(strips, chunks), WAVE_NT, smem, stream>>>(p);
+    PCD_LAUNCHED();
+    return PCD_OK;
+}
+
+// One pass over global rows [row_first, row_first+rows): phi_out <- nsweeps (<= TILED_TS) sweeps applied to
+// phi_in.  Arrays have local row 0 = global row grow0 and must hold rows row_first-2*nsweeps-1 ..
+// row_first+rows+2*nsweeps-1 (clipped to the grid) of the current field.
+int tiled_pass(const double *phi_in, double *phi_out, const double *D, int W, int H, int row_first, int rows, int grow0,
+               int nsweeps, unsigned long long *slots, cudaStream_t stream) {
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        PCD_CUDA(cudaGetDevice(&dev));
+        PCD_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    WaveParams prm;
+    prm.phi_in = phi_in; prm.phi_out = phi_out; prm.D = D; prm.W = W; prm.H = H;
+    prm.row_first = row_first; prm.rows = rows; prm.grow0 = grow0; prm.chunk_rows = rows;
+    prm.w = make_w(W); prm.slots = slots;
+    if (nsweeps >= 2) return launch_wave<2>(prm, sm_count, stream);
+    return launch_wave<1>(prm, sm_count, stream);
+}
+
+}  // namespace pcd

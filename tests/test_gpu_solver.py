@@ -11,11 +11,11 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-PATHS = ["streaming", "resident"]
+PATHS = ["streaming", "resident", "tiled"]
 
 
 def path_id(pcd, name):
-    return {"streaming": pcd.SOLVER_STREAMING, "resident": pcd.SOLVER_RESIDENT}[name]
+    return {"streaming": pcd.SOLVER_STREAMING, "resident": pcd.SOLVER_RESIDENT, "tiled": pcd.SOLVER_TILED}[name]
 
 
 def run_gpu(pcd, D, phi0, max_it, tol, path, lag=0):

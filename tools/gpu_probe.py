@@ -9,7 +9,7 @@ path = sys.argv[1] if len(sys.argv) > 1 else "resident"
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 H = int(sys.argv[3]) if len(sys.argv) > 3 else W
 sweeps = int(sys.argv[4]) if len(sys.argv) > 4 else 1000
-pid = {"streaming": P.SOLVER_STREAMING, "resident": P.SOLVER_RESIDENT, "auto": P.SOLVER_AUTO}[path]
+pid = {"streaming": P.SOLVER_STREAMING, "resident": P.SOLVER_RESIDENT, "auto": P.SOLVER_AUTO, "tiled": P.SOLVER_TILED}[path]
 rng = np.random.RandomState(0)
 D = rng.standard_normal((H, W)); D -= D.mean()
 s = P.Solver(W, H, 0, pid)
