@@ -147,17 +147,25 @@ int pcd_solver_run(pcd_solver *s, int max_iterations, double convergence_thresho
 int pcd_solver_path_used(const pcd_solver *s);
 
 /* ---- row-slab solver for multi-GPU runs (no counterpart in the reference) -------------------
- * One process per GPU owns global rows [row0, row0+rows) of a width x height grid plus one ghost row above
- * and below (local row r <-> global row row0+r-1).  The host layer (poisson_caustic_design_b200/slab.py,
- * torch.distributed) exchanges the boundary rows between colour phases and all-reduces the per-sweep max.
- * `cuda_stream` is the caller's stream (torch's current stream) so kernels and collectives order naturally. */
+ * One process per GPU owns global rows [row0, row0+rows) of a width x height grid plus GH =
+ * pcd_slab_ghost_rows() ghost rows above and below (local row r <-> global row row0-GH+r).  The host layer
+ * (poisson_caustic_design_b200/slab.py, torch.distributed) refreshes the ghost rows from the neighbouring ranks --
+ * GH rows after every wavefront pass (pcd_slab_pass: up to pcd_slab_sweeps_per_pass() sweeps, the field
+ * ping-pongs between two buffers) or one row after every colour phase (pcd_slab_sweep_colour, the NaN-hole path)
+ * -- and all-reduces the per-sweep max.  `cuda_stream` is the caller's stream (torch's current stream) so
+ * kernels and collectives order naturally. */
 typedef struct pcd_slab pcd_slab;
+int pcd_slab_ghost_rows(void);
+int pcd_slab_sweeps_per_pass(void);
 int pcd_slab_create(int width, int height, int row0, int rows, int device, void *cuda_stream, pcd_slab **out);
 void pcd_slab_destroy(pcd_slab *s);
-int pcd_slab_device_ptrs(pcd_slab *s, void **phi_dev, void **D_dev, void **sweep_max_dev);
+int pcd_slab_device_ptrs(pcd_slab *s, void **phi0_dev, void **phi1_dev, void **sweep_max_dev);
+int pcd_slab_current(const pcd_slab *s);   /* which of the two phi buffers holds the field */
+int pcd_slab_has_nan(const pcd_slab *s);   /* D (owned rows and their neighbours) contains NaN */
 int pcd_slab_upload(pcd_slab *s, const double *D_rows_with_ghosts, const double *phi_rows_with_ghosts);
 int pcd_slab_download(pcd_slab *s, double *phi_owned_rows);
 int pcd_slab_sweep_colour(pcd_slab *s, int colour, int slot);
+int pcd_slab_pass(pcd_slab *s, int nsweeps, int slot);
 int pcd_slab_clear_max(pcd_slab *s, int n_slots);
 
 #ifdef __cplusplus

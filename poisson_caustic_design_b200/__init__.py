@@ -96,6 +96,11 @@ ABI = [
     ("pcd_slab_upload", C.c_int, [C.c_void_p, _dp, _dp]),
     ("pcd_slab_download", C.c_int, [C.c_void_p, _dp]),
     ("pcd_slab_sweep_colour", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("pcd_slab_pass", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("pcd_slab_ghost_rows", C.c_int, []),
+    ("pcd_slab_sweeps_per_pass", C.c_int, []),
+    ("pcd_slab_current", C.c_int, [C.c_void_p]),
+    ("pcd_slab_has_nan", C.c_int, [C.c_void_p]),
     ("pcd_slab_clear_max", C.c_int, [C.c_void_p, C.c_int]),
 ]
 

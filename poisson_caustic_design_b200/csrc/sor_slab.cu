@@ -1,42 +1,53 @@
 // K-SOR on a ROW SLAB of a larger grid (multi-GPU): the process owns global rows
-// [row0, row0+rows) of a W x H grid plus one ghost row above and below (local row r <-> global row
-// row0 + r - 1).  One launch updates the cells of one colour of the owned rows; the host layer exchanges
-// the two boundary rows with the neighbouring ranks between colour phases (torch.distributed / NCCL over
-// NVLink) and all-reduces the per-sweep max.  The per-cell arithmetic is sor_colour_kernel's, so a
-// G-slab solve is bit-identical to the single-GPU solve (red-black updates of one colour are
-// order-independent and max is exact).
+// [row0, row0+rows) of a W x H grid plus GH ghost rows above and below (local row r <-> global row
+// row0 - GH + r).  Two ways to advance:
+//   * pcd_slab_pass        : one wavefront pass (sor_tiled.cu) = up to TS full sweeps, field ping-pongs between
+//                            two buffers; afterwards the host layer refreshes the GH ghost rows from the
+//                            neighbouring ranks (one exchange per TS sweeps, GH = 2*TS+1 rows each way);
+//   * pcd_slab_sweep_colour: one colour phase in place (masked kernel; the NaN-hole path), one ghost row
+//                            exchanged per phase.
+// The host layer (slab.py, torch.distributed: NCCL over NVLink, gloo in CPU tests) does the exchanges and
+// all-reduces the per-sweep max.  Per-cell arithmetic is the single-GPU kernels', so a G-slab solve is
+// bit-identical to the single-GPU solve (red-black updates of one colour are order-independent, max is exact).
 #include "sor_common.cuh"
 
 struct pcd_slab {
-    int W = 0, H = 0, row0 = 0, rows = 0, device = 0;
+    int W = 0, H = 0, row0 = 0, rows = 0, device = 0, GH = 0;
     cudaStream_t stream = nullptr;   // caller's stream (e.g. torch's current stream), never owned
-    double *phi = nullptr, *D = nullptr;            // (rows+2) x W each
-    unsigned char *mask = nullptr;                  // (rows+2) x W neighbour masks (always built: D never changes)
+    double *phi[2] = {nullptr, nullptr};  // (rows + 2*GH) x W each; phi[cur] holds the field
+    double *D = nullptr;
+    int cur = 0;
+    unsigned char *mask = nullptr;                  // neighbour masks (colour path)
     unsigned long long *sweep_max = nullptr;        // [ring]
+    int *d_flag = nullptr;
+    int has_nan = 0;
     int ring = 0;
     long long launches = 0;
 };
 
 namespace pcd {
 
-__global__ void slab_mask_kernel(const double *__restrict__ D, unsigned char *__restrict__ mask, int W, int H, int row0, int rows) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y + 1;  // owned local rows 1..rows
+__global__ void slab_mask_kernel(const double *__restrict__ D, unsigned char *__restrict__ mask, int W, int H, int row0,
+                                 int rows, int GH, int *__restrict__ nan_flag) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y + GH;  // owned local rows GH..GH+rows-1
     if (x >= W) return;
-    const int gy = row0 + r - 1;
+    const int gy = row0 + r - GH;
     const size_t i = (size_t)r * W + x;
     unsigned m = 0;
-    if (x != 0 && !isnan(D[i - 1])) m |= 1;
-    if (gy != 0 && !isnan(D[i - W])) m |= 2;
-    if (x != W - 1 && !isnan(D[i + 1])) m |= 4;
-    if (gy != H - 1 && !isnan(D[i + W])) m |= 8;
+    bool any_nan = isnan(D[i]);
+    if (x != 0) { if (!isnan(D[i - 1])) m |= 1; else any_nan = true; }
+    if (gy != 0) { if (!isnan(D[i - W])) m |= 2; else any_nan = true; }
+    if (x != W - 1) { if (!isnan(D[i + 1])) m |= 4; else any_nan = true; }
+    if (gy != H - 1) { if (!isnan(D[i + W])) m |= 8; else any_nan = true; }
     mask[i] = (unsigned char)m;
+    if (any_nan) atomicOr(nan_flag, 1);
 }
 
 __global__ void __launch_bounds__(256)
 sor_slab_colour_kernel(double *__restrict__ phi, const double *__restrict__ D, const unsigned char *__restrict__ mask,
-                       int W, int row0, int colour, SorW w, unsigned long long *__restrict__ slot) {
-    const int r = blockIdx.y + 1;
-    const int gy = row0 + r - 1;
+                       int W, int row0, int GH, int colour, SorW w, unsigned long long *__restrict__ slot) {
+    const int r = blockIdx.y + GH;
+    const int gy = row0 + r - GH;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int x = 2 * k + ((gy + colour) & 1);
     double a = 0.0;
@@ -72,6 +83,9 @@ using namespace pcd;
 
 extern "C" {
 
+int pcd_slab_ghost_rows(void) { return 2 * tiled_sweeps_per_pass() + 1; }
+int pcd_slab_sweeps_per_pass(void) { return tiled_sweeps_per_pass(); }
+
 int pcd_slab_create(int width, int height, int row0, int rows, int device, void *cuda_stream, pcd_slab **out) {
     if (!out) { set_error("null argument"); return PCD_ERR_INVALID; }
     *out = nullptr;
@@ -82,20 +96,25 @@ int pcd_slab_create(int width, int height, int row0, int rows, int device, void 
     PCD_TRY(select_device(device));
     pcd_slab *s = new pcd_slab();
     s->W = width; s->H = height; s->row0 = row0; s->rows = rows; s->device = device;
+    s->GH = pcd_slab_ghost_rows();
     s->stream = (cudaStream_t)cuda_stream;
     s->ring = 4096;
-    const size_t n = (size_t)(rows + 2) * width;
-    cudaError_t e = cudaMalloc(&s->phi, n * sizeof(double));
+    const size_t n = (size_t)(rows + 2 * s->GH) * width;
+    cudaError_t e = cudaMalloc(&s->phi[0], n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&s->phi[1], n * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&s->D, n * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&s->mask, n);
     if (e == cudaSuccess) e = cudaMalloc(&s->sweep_max, sizeof(unsigned long long) * s->ring);
-    if (e == cudaSuccess) e = cudaMemset(s->phi, 0, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_flag, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(s->phi[0], 0, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(s->phi[1], 0, n * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(s->D, 0, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(s->mask, 0, n);
     if (e == cudaSuccess) e = cudaMemset(s->sweep_max, 0, sizeof(unsigned long long) * s->ring);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         set_error("slab allocation failed: %s", cudaGetErrorString(e));
-        cudaFree(s->phi); cudaFree(s->D); cudaFree(s->mask); cudaFree(s->sweep_max);
+        cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->D); cudaFree(s->mask); cudaFree(s->sweep_max); cudaFree(s->d_flag);
         delete s;
         return PCD_ERR_CUDA;
     }
@@ -106,31 +125,40 @@ int pcd_slab_create(int width, int height, int row0, int rows, int device, void 
 void pcd_slab_destroy(pcd_slab *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    cudaFree(s->phi); cudaFree(s->D); cudaFree(s->mask); cudaFree(s->sweep_max);
+    cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->D); cudaFree(s->mask); cudaFree(s->sweep_max); cudaFree(s->d_flag);
     delete s;
 }
 
-int pcd_slab_device_ptrs(pcd_slab *s, void **phi_dev, void **D_dev, void **sweep_max_dev) {
+int pcd_slab_device_ptrs(pcd_slab *s, void **phi0_dev, void **phi1_dev, void **sweep_max_dev) {
     if (!s) { set_error("null slab"); return PCD_ERR_INVALID; }
-    if (phi_dev) *phi_dev = s->phi;
-    if (D_dev) *D_dev = s->D;
+    if (phi0_dev) *phi0_dev = s->phi[0];
+    if (phi1_dev) *phi1_dev = s->phi[1];
     if (sweep_max_dev) *sweep_max_dev = s->sweep_max;
     return PCD_OK;
 }
 
-// D_rows / phi_rows: host arrays of (rows+2) x W doubles INCLUDING the two ghost rows (ghost rows outside the
+int pcd_slab_current(const pcd_slab *s) { return s ? s->cur : -1; }
+int pcd_slab_has_nan(const pcd_slab *s) { return s ? s->has_nan : -1; }
+
+// D_rows / phi_rows: host arrays of (rows + 2*GH) x W doubles INCLUDING the ghost rows (ghost rows outside the
 // grid are ignored); either may be NULL.
 int pcd_slab_upload(pcd_slab *s, const double *D_rows, const double *phi_rows) {
     if (!s) { set_error("null slab"); return PCD_ERR_INVALID; }
     PCD_TRY(select_device(s->device));
-    const size_t bytes = (size_t)(s->rows + 2) * s->W * sizeof(double);
+    const size_t bytes = (size_t)(s->rows + 2 * s->GH) * s->W * sizeof(double);
     if (D_rows) {
         PCD_CUDA(cudaMemcpyAsync(s->D, D_rows, bytes, cudaMemcpyHostToDevice, s->stream));
-        slab_mask_kernel<<<dim3((s->W + 255) / 256, s->rows), 256, 0, s->stream>>>(s->D, s->mask, s->W, s->H, s->row0, s->rows);
+        PCD_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
+        slab_mask_kernel<<<dim3((s->W + 255) / 256, s->rows), 256, 0, s->stream>>>(s->D, s->mask, s->W, s->H, s->row0, s->rows,
+                                                                                 s->GH, s->d_flag);
         PCD_LAUNCHED();
         s->launches++;
+        PCD_CUDA(cudaMemcpyAsync(&s->has_nan, s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     }
-    if (phi_rows) PCD_CUDA(cudaMemcpyAsync(s->phi, phi_rows, bytes, cudaMemcpyHostToDevice, s->stream));
+    if (phi_rows) {
+        PCD_CUDA(cudaMemcpyAsync(s->phi[0], phi_rows, bytes, cudaMemcpyHostToDevice, s->stream));
+        s->cur = 0;
+    }
     PCD_CUDA(cudaStreamSynchronize(s->stream));
     return PCD_OK;
 }
@@ -138,18 +166,34 @@ int pcd_slab_upload(pcd_slab *s, const double *D_rows, const double *phi_rows) {
 int pcd_slab_download(pcd_slab *s, double *phi_owned_rows) {
     if (!s || !phi_owned_rows) { set_error("null argument"); return PCD_ERR_INVALID; }
     PCD_TRY(select_device(s->device));
-    PCD_CUDA(cudaMemcpyAsync(phi_owned_rows, s->phi + s->W, (size_t)s->rows * s->W * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    PCD_CUDA(cudaMemcpyAsync(phi_owned_rows, s->phi[s->cur] + (size_t)s->GH * s->W, (size_t)s->rows * s->W * sizeof(double),
+                             cudaMemcpyDeviceToHost, s->stream));
     PCD_CUDA(cudaStreamSynchronize(s->stream));
     return PCD_OK;
 }
 
-// one colour phase of sweep slot `slot` (0 <= slot < 4096); asynchronous on the slab's stream
+// one colour phase of sweep slot `slot` (0 <= slot < 4096) in place on the current buffer; asynchronous
 int pcd_slab_sweep_colour(pcd_slab *s, int colour, int slot) {
     if (!s || slot < 0 || slot >= s->ring) { set_error("bad slab / slot"); return PCD_ERR_INVALID; }
     const int K = (s->W + 1) / 2;
-    sor_slab_colour_kernel<<<dim3((K + 255) / 256, s->rows), 256, 0, s->stream>>>(s->phi, s->D, s->mask, s->W, s->row0, colour,
-                                                                                   make_w(s->W), s->sweep_max + slot);
+    sor_slab_colour_kernel<<<dim3((K + 255) / 256, s->rows), 256, 0, s->stream>>>(s->phi[s->cur], s->D, s->mask, s->W, s->row0,
+                                                                                   s->GH, colour, make_w(s->W), s->sweep_max + slot);
     PCD_LAUNCHED();
+    s->launches++;
+    return PCD_OK;
+}
+
+// one wavefront pass: nsweeps (<= pcd_slab_sweeps_per_pass()) full sweeps, maxima into slots [slot, slot+nsweeps);
+// the field moves to the other buffer.  Requires valid ghost rows and no NaN in D.
+int pcd_slab_pass(pcd_slab *s, int nsweeps, int slot) {
+    if (!s || slot < 0 || slot + nsweeps > s->ring || nsweeps < 1 || nsweeps > tiled_sweeps_per_pass()) {
+        set_error("bad slab / slot / sweep count");
+        return PCD_ERR_INVALID;
+    }
+    if (s->has_nan) { set_error("pcd_slab_pass: D has NaN holes, use the colour path"); return PCD_ERR_UNSUPPORTED; }
+    PCD_TRY(tiled_pass(s->phi[s->cur], s->phi[s->cur ^ 1], s->D, s->W, s->H, s->row0, s->rows, s->row0 - s->GH, nsweeps,
+                       s->sweep_max + slot, s->stream));
+    s->cur ^= 1;
     s->launches++;
     return PCD_OK;
 }

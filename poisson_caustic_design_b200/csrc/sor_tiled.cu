@@ -25,7 +25,7 @@
 namespace pcd {
 
 constexpr int WAVE_NT = 256;  // threads = column pairs per strip window
-constexpr int WAVE_PF = 4;    // rows prefetched ahead by cp.async
+constexpr int WAVE_PF = 3;    // rows prefetched ahead by cp.async
 
 template <int TS>
 struct WaveCfg {
@@ -259,8 +259,9 @@ static int launch_wave(const WaveParams &prm, int sm_count, cudaStream_t stream)
     }
     WaveParams p = prm;
     const int strips = (p.W + Cfg::CORE - 1) / Cfg::CORE;
-    // about two CTAs per SM; chunks long enough that the 2*NP warm-up rows stay a small fraction
-    int chunks = (2 * sm_count + strips - 1) / strips;
+    // ONE wave of two CTAs per SM (never a second, nearly empty wave); chunks long enough that the 2*NP warm-up
+    // rows stay a small fraction
+    int chunks = (2 * sm_count) / strips;
     const int min_rows = 16 * Cfg::NP;
     if (chunks * min_rows > p.rows) chunks = p.rows / min_rows;
     if (chunks < 1) chunks = 1;

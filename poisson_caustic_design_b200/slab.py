@@ -1,13 +1,18 @@
 """Row-slab Poisson solve across GPUs: one process per GPU, torch.distributed for the plumbing.
 
-The W x H grid is cut into `world` contiguous row slabs.  Per red-black colour phase every rank updates its
-rows (CUDA: ``pcd_slab_sweep_colour``), then swaps one boundary row with each neighbour (NCCL send/recv over
-NVLink; gloo in the CPU tests); every ``check_every`` sweeps the per-sweep maxima are all-reduced (MAX) and
-every rank takes the same stop decision.  Updates of one colour are order-independent and max is exact, so
-the result is bit-identical to the single-GPU solve run for the same number of sweeps.
+The W x H grid is cut into `world` contiguous row slabs, each held with GH ghost rows above and below.
+Two ways to advance, both bit-identical to the single-GPU solve run for the same number of sweeps (updates of
+one colour are order-independent, max is exact):
 
-``engine`` abstracts the local slab (CudaSlabEngine below; the CPU tests plug a numpy engine in to exercise
-this host logic without a GPU).
+* wavefront mode (default): ``engine.pass_`` runs up to TS full red-black sweeps over the slab in one kernel
+  (temporal blocking, csrc/sor_tiled.cu); afterwards every rank sends its GH boundary rows to each neighbour
+  (NCCL send/recv over NVLink; gloo in the CPU tests) -- ONE exchange per TS sweeps;
+* colour mode (D has NaN holes, or slabs thinner than GH rows): one kernel per colour phase, one ghost row
+  exchanged per phase.
+
+Every ``check_every`` sweeps the per-sweep maxima are all-reduced (MAX) and every rank takes the same stop
+decision.  ``engine`` abstracts the local slab (CudaSlabEngine below; the CPU tests plug a numpy engine in to
+exercise this host logic without a GPU).
 """
 from __future__ import annotations
 
@@ -24,12 +29,12 @@ def partition(H: int, world: int, rank: int):
     return row0, (rank + 1) * H // world - row0
 
 
-def with_ghosts(a: np.ndarray, row0: int, rows: int) -> np.ndarray:
-    """Rows row0-1 .. row0+rows of a global [H, W] array; ghost rows outside the grid are zero."""
+def with_ghosts(a: np.ndarray, row0: int, rows: int, gh: int = 1) -> np.ndarray:
+    """Rows row0-gh .. row0+rows+gh-1 of a global [H, W] array; ghost rows outside the grid are zero."""
     H, W = a.shape
-    out = np.zeros((rows + 2, W), dtype=np.float64)
-    lo, hi = max(row0 - 1, 0), min(row0 + rows + 1, H)
-    out[lo - (row0 - 1): hi - (row0 - 1)] = a[lo:hi]
+    out = np.zeros((rows + 2 * gh, W), dtype=np.float64)
+    lo, hi = max(row0 - gh, 0), min(row0 + rows + gh, H)
+    out[lo - (row0 - gh): hi - (row0 - gh)] = a[lo:hi]
     return out
 
 
@@ -46,14 +51,18 @@ class CudaSlabEngine:
     def __init__(self, W: int, H: int, row0: int, rows: int, device: int):
         import torch
         self.W, self.H, self.row0, self.rows, self.device = W, H, row0, rows, device
+        self.GH = lib().pcd_slab_ghost_rows()
+        self.TS = lib().pcd_slab_sweeps_per_pass()
         torch.cuda.set_device(device)
         self._h = C.c_void_p()
         stream = torch.cuda.current_stream(device).cuda_stream
         _check(lib().pcd_slab_create(W, H, row0, rows, device, C.c_void_p(stream), C.byref(self._h)))
-        phi, D, mx = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        _check(lib().pcd_slab_device_ptrs(self._h, C.byref(phi), C.byref(D), C.byref(mx)))
+        p0, p1, mx = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib().pcd_slab_device_ptrs(self._h, C.byref(p0), C.byref(p1), C.byref(mx)))
         dev = torch.device("cuda", device)
-        self.phi = torch.as_tensor(_DevView(phi.value, (rows + 2, W), "<f8"), device=dev)
+        shape = (rows + 2 * self.GH, W)
+        self._phi = [torch.as_tensor(_DevView(p0.value, shape, "<f8"), device=dev),
+                     torch.as_tensor(_DevView(p1.value, shape, "<f8"), device=dev)]
         self._max = torch.as_tensor(_DevView(mx.value, (4096,), "<f8"), device=dev)  # bit patterns of doubles >= 0
 
     def close(self):
@@ -61,11 +70,23 @@ class CudaSlabEngine:
             lib().pcd_slab_destroy(self._h)
             self._h = C.c_void_p()
 
+    @property
+    def phi(self):
+        """[rows + 2*GH, W] view of the buffer that currently holds the field."""
+        return self._phi[lib().pcd_slab_current(self._h)]
+
+    @property
+    def has_nan(self) -> bool:
+        return bool(lib().pcd_slab_has_nan(self._h))
+
     def upload(self, D_g: np.ndarray, phi_g: np.ndarray):
         _check(lib().pcd_slab_upload(self._h, _p(np.ascontiguousarray(D_g)), _p(np.ascontiguousarray(phi_g))))
 
     def sweep_colour(self, colour: int, slot: int):
         _check(lib().pcd_slab_sweep_colour(self._h, colour, slot))
+
+    def pass_(self, nsweeps: int, slot: int):
+        _check(lib().pcd_slab_pass(self._h, nsweeps, slot))
 
     def clear_max(self, n: int):
         _check(lib().pcd_slab_clear_max(self._h, n))
@@ -79,78 +100,118 @@ class CudaSlabEngine:
         return out
 
 
-def _exchange(engine, dist, rank: int, world: int):
-    """Swap boundary rows with the neighbouring ranks: owned row 1 -> upper neighbour's lower ghost,
-    owned row `rows` -> lower neighbour's upper ghost."""
+def _exchange(engine, dist, rank: int, world: int, depth: int):
+    """Refresh `depth` ghost rows on each side: my top `depth` owned rows -> upper neighbour's lower ghosts,
+    my bottom `depth` owned rows -> lower neighbour's upper ghosts."""
     ops = []
-    phi, rows = engine.phi, engine.rows
+    phi, rows, GH = engine.phi, engine.rows, engine.GH
     if rank > 0:
-        ops.append(dist.P2POp(dist.isend, phi[1], rank - 1))
-        ops.append(dist.P2POp(dist.irecv, phi[0], rank - 1))
+        ops.append(dist.P2POp(dist.isend, phi[GH:GH + depth], rank - 1))
+        ops.append(dist.P2POp(dist.irecv, phi[GH - depth:GH], rank - 1))
     if rank < world - 1:
-        ops.append(dist.P2POp(dist.isend, phi[rows], rank + 1))
-        ops.append(dist.P2POp(dist.irecv, phi[rows + 1], rank + 1))
+        ops.append(dist.P2POp(dist.isend, phi[GH + rows - depth:GH + rows], rank + 1))
+        ops.append(dist.P2POp(dist.irecv, phi[GH + rows:GH + rows + depth], rank + 1))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
 
 
-def solve(engine, dist, rank: int, world: int, max_iterations: int, tol: float, check_every: int = 64):
-    """Distributed red-black SOR.  Returns {"sweeps", "converged_at", "last_max_update"} (same on all ranks)."""
+def _decide(m_host: np.ndarray, tol: float, done: int):
+    below = np.nonzero(m_host < tol)[0]
+    if below.size:
+        return done + int(below[0]) + 1, float(m_host[below[0]])
+    return 0, float(m_host[-1])
+
+
+def use_wavefront(engine, dist, world: int, min_rows: int) -> bool:
+    """Same answer on every rank: no NaN anywhere and every slab at least GH rows thick."""
     import torch
+    ok = int((not engine.has_nan) and hasattr(engine, "pass_") and min_rows >= engine.GH)
+    if world > 1:
+        t = torch.tensor([ok], dtype=torch.int32, device=engine.phi.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = int(t.item())
+    return bool(ok)
+
+
+def solve(engine, dist, rank: int, world: int, max_iterations: int, tol: float, check_every: int = 64, mode: str = "auto"):
+    """Distributed red-black SOR.  Returns {"sweeps", "converged_at", "last_max_update", "mode"} (same on all ranks)."""
+    import torch
+    H = engine.H
+    min_rows = min(partition(H, world, r)[1] for r in range(world))
+    wave = use_wavefront(engine, dist, world, min_rows) if mode == "auto" else (mode == "wavefront")
+    TS = engine.TS if wave else 1
+    check_every = max(TS, min(check_every, 4096))
+    check_every = (check_every + TS - 1) // TS * TS
     done, conv, last = 0, 0, 0.0
-    check_every = max(1, min(check_every, 4096))
     while done < max_iterations and not conv:
         k = min(check_every, max_iterations - done)
         engine.clear_max(k)
-        for j in range(k):
-            for colour in (0, 1):
-                engine.sweep_colour(colour, j)
+        if wave:
+            j = 0
+            while j < k:
+                ns = min(TS, k - j)
+                engine.pass_(ns, j)
                 if world > 1:
-                    _exchange(engine, dist, rank, world)
+                    _exchange(engine, dist, rank, world, engine.GH)
+                j += ns
+        else:
+            for j in range(k):
+                for colour in (0, 1):
+                    engine.sweep_colour(colour, j)
+                    if world > 1:
+                        _exchange(engine, dist, rank, world, 1)
         m = engine.max_tensor(k).clone()
         if world > 1:
             dist.all_reduce(m, op=dist.ReduceOp.MAX)
         m_host = m.cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
-        below = np.nonzero(m_host < tol)[0]
-        if below.size:
-            conv = done + int(below[0]) + 1
-            last = float(m_host[below[0]])
-        else:
-            last = float(m_host[-1])
+        conv, last = _decide(m_host, tol, done)
         done += k
-    return {"sweeps": done, "converged_at": conv, "last_max_update": last}
+    return {"sweeps": done, "converged_at": conv, "last_max_update": last, "mode": "wavefront" if wave else "colour"}
 
 
-def solve_local(engines, max_iterations: int, tol: float, check_every: int = 64):
+def solve_local(engines, max_iterations: int, tol: float, check_every: int = 64, mode: str = "auto"):
     """Single-process emulation of G slabs (all engines in this process, e.g. G slabs on ONE GPU): same phase
-    structure as `solve`, halo rows copied directly between the engines."""
+    structure as `solve`, ghost rows copied directly between the engines."""
     import torch
     G = len(engines)
+    e0 = engines[0]
+    min_rows = min(e.rows for e in engines)
+    wave = (mode == "wavefront") or (mode == "auto" and all((not e.has_nan) and hasattr(e, "pass_") for e in engines)
+                                     and min_rows >= e0.GH)
+    TS = e0.TS if wave else 1
+    check_every = max(TS, min(check_every, 4096))
+    check_every = (check_every + TS - 1) // TS * TS
+
+    def exchange(depth):
+        for g in range(G - 1):
+            up, dn = engines[g], engines[g + 1]
+            GH = up.GH
+            dn.phi[GH - depth:GH].copy_(up.phi[GH + up.rows - depth:GH + up.rows])
+            up.phi[GH + up.rows:GH + up.rows + depth].copy_(dn.phi[GH:GH + depth])
+
     done, conv, last = 0, 0, 0.0
-    check_every = max(1, min(check_every, 4096))
     while done < max_iterations and not conv:
         k = min(check_every, max_iterations - done)
         for e in engines:
             e.clear_max(k)
-        for j in range(k):
-            for colour in (0, 1):
+        if wave:
+            j = 0
+            while j < k:
+                ns = min(TS, k - j)
                 for e in engines:
-                    e.sweep_colour(colour, j)
-                for g in range(G - 1):
-                    up, dn = engines[g], engines[g + 1]
-                    dn.phi[0].copy_(up.phi[up.rows])
-                    up.phi[up.rows + 1].copy_(dn.phi[1])
-        ms = [e.max_tensor(k) for e in engines]
-        m = ms[0].clone()
-        for other in ms[1:]:
-            m = torch.maximum(m, other.to(m.device)) if isinstance(m, torch.Tensor) else np.maximum(m, other)
-        m_host = m.cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
-        below = np.nonzero(m_host < tol)[0]
-        if below.size:
-            conv = done + int(below[0]) + 1
-            last = float(m_host[below[0]])
+                    e.pass_(ns, j)
+                exchange(e0.GH)
+                j += ns
         else:
-            last = float(m_host[-1])
+            for j in range(k):
+                for colour in (0, 1):
+                    for e in engines:
+                        e.sweep_colour(colour, j)
+                    exchange(1)
+        m = engines[0].max_tensor(k).clone()
+        for e in engines[1:]:
+            m = torch.maximum(m, e.max_tensor(k).to(m.device))
+        conv, last = _decide(m.cpu().numpy(), tol, done)
         done += k
-    return {"sweeps": done, "converged_at": conv, "last_max_update": last}
+    return {"sweeps": done, "converged_at": conv, "last_max_update": last, "mode": "wavefront" if wave else "colour"}

@@ -23,29 +23,31 @@ def single_gpu(pcd, D, phi0, sweeps):
     return out, info
 
 
+@pytest.mark.parametrize("holes", [False, True])
 @pytest.mark.parametrize("G", [1, 2, 5])
-def test_slabs_on_one_gpu_bit_identical(pcd, port, G):
+def test_slabs_on_one_gpu_bit_identical(pcd, port, G, holes):
     from poisson_caustic_design_b200 import slab
     rng = np.random.RandomState(G)
     H, W = 203, 150
     D = rng.standard_normal((H, W))
-    D[50:60, 70:90] = np.nan
+    if holes:
+        D[50:60, 70:90] = np.nan                      # NaN holes -> colour mode (masked kernels)
     D[np.isfinite(D)] -= D[np.isfinite(D)].mean()
     phi0 = rng.standard_normal((H, W))
     engines = []
     for g in range(G):
         row0, rows = slab.partition(H, G, g)
         e = slab.CudaSlabEngine(W, H, row0, rows, 0)
-        e.upload(slab.with_ghosts(D, row0, rows), slab.with_ghosts(phi0, row0, rows))
+        e.upload(slab.with_ghosts(D, row0, rows, e.GH), slab.with_ghosts(phi0, row0, rows, e.GH))
         engines.append(e)
-    info = slab.solve_local(engines, 40, 0.0, 16)
+    info = slab.solve_local(engines, 41, 0.0, 16)
     got = np.concatenate([e.download() for e in engines], axis=0)
     for e in engines:
         e.close()
-    want, winfo = single_gpu(pcd, D, phi0, 40)
-    assert info["sweeps"] == 40
+    want, winfo = single_gpu(pcd, D, phi0, 41)
+    assert info["sweeps"] == 41 and info["mode"] == ("colour" if holes else "wavefront")
     assert np.array_equal(got, want, equal_nan=True)
-    assert np.array_equal(got, port.poisson_rb(D, phi0, 40, 0.0)[0], equal_nan=True)
+    assert np.array_equal(got, port.poisson_rb(D, phi0, 41, 0.0)[0], equal_nan=True)
     assert info["last_max_update"] == winfo["last_max_update"]
 
 
@@ -60,7 +62,7 @@ def test_slab_stopping_rule_matches_single_gpu(pcd, port):
     for g in range(3):
         row0, rows = slab.partition(H, 3, g)
         e = slab.CudaSlabEngine(W, H, row0, rows, 0)
-        e.upload(slab.with_ghosts(D, row0, rows), slab.with_ghosts(z, row0, rows))
+        e.upload(slab.with_ghosts(D, row0, rows, e.GH), slab.with_ghosts(z, row0, rows, e.GH))
         engines.append(e)
     info = slab.solve_local(engines, 100000, 1e-7, 32)
     got = np.concatenate([e.download() for e in engines], axis=0)

@@ -15,7 +15,7 @@ from conftest import ROOT
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def _worker(rank, world, port, D, phi0, max_it, tol, check_every, out_dir):
+def _worker(rank, world, port, D, phi0, max_it, tol, check_every, out_dir, mode):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from poisson_caustic_design_b200 import slab
@@ -26,15 +26,16 @@ def _worker(rank, world, port, D, phi0, max_it, tol, check_every, out_dir):
     H, W = D.shape
     row0, rows = slab.partition(H, world, rank)
     eng = NumpySlabEngine(W, H, row0, rows)
-    eng.upload(slab.with_ghosts(D, row0, rows), slab.with_ghosts(phi0, row0, rows))
-    info = slab.solve(eng, dist, rank, world, max_it, tol, check_every)
+    eng.upload(slab.with_ghosts(D, row0, rows, eng.GH), slab.with_ghosts(phi0, row0, rows, eng.GH))
+    info = slab.solve(eng, dist, rank, world, max_it, tol, check_every, mode)
+    assert info["mode"] == ("colour" if (mode == "colour" or np.isnan(D).any()) else "wavefront")
     np.save(os.path.join(out_dir, f"phi_{rank}.npy"), eng.download())
     np.save(os.path.join(out_dir, f"info_{rank}.npy"), np.array([info["sweeps"], info["converged_at"], info["last_max_update"]]))
     dist.destroy_process_group()
 
 
-def run_world(world, D, phi0, max_it, tol, check_every, tmp_path, port):
-    mp.spawn(_worker, args=(world, port, D, phi0, max_it, tol, check_every, str(tmp_path)), nprocs=world, join=True)
+def run_world(world, D, phi0, max_it, tol, check_every, tmp_path, port, mode="auto"):
+    mp.spawn(_worker, args=(world, port, D, phi0, max_it, tol, check_every, str(tmp_path), mode), nprocs=world, join=True)
     phi = np.concatenate([np.load(tmp_path / f"phi_{r}.npy") for r in range(world)], axis=0)
     infos = [np.load(tmp_path / f"info_{r}.npy") for r in range(world)]
     for i in infos[1:]:
@@ -53,6 +54,24 @@ def test_partition_covers_the_grid():
             assert max(p[1] for p in parts) - min(p[1] for p in parts) <= 1
     g = slab.with_ghosts(np.arange(12.0).reshape(4, 3), 0, 2)
     assert g.shape == (4, 3) and not g[0].any() and np.array_equal(g[1:], np.arange(9.0).reshape(3, 3))
+    g = slab.with_ghosts(np.arange(12.0).reshape(4, 3), 2, 2, 5)
+    assert g.shape == (12, 3) and not g[:3].any() and not g[7:].any() and np.array_equal(g[3:7], np.arange(12.0).reshape(4, 3))
+
+
+@pytest.mark.parametrize("mode", ["wavefront", "colour"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_slabs_without_holes(port, world, mode, tmp_path):
+    """Both ways to advance (TS sweeps per pass + GH-row exchange; one colour phase + one-row exchange)."""
+    rng = np.random.RandomState(10 * world)
+    H, W = 41, 30                                     # uneven partition, slabs >= GH rows
+    D = rng.standard_normal((H, W))
+    D -= D.mean()
+    phi0 = rng.standard_normal((H, W))
+    phi, info = run_world(world, D, phi0, 23, 0.0, 8, tmp_path, 29700 + 10 * world + (mode == "colour"), mode)
+    want, n, conv, last = port.poisson_rb(D, phi0, 23, 0.0)     # 23: the last pass is a partial one
+    assert int(info[0]) == 23 and int(info[1]) == 0
+    assert np.array_equal(phi, want)
+    assert info[2] == last
 
 
 @pytest.mark.parametrize("world", [2, 3])

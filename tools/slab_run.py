@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--tol", type=float, default=0.0)
     ap.add_argument("--check_every", type=int, default=64)
     ap.add_argument("--out", default="")
+    ap.add_argument("--mode", default="auto", choices=["auto", "wavefront", "colour"])
     a = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
@@ -33,15 +34,15 @@ def main():
     phi0 = np.zeros_like(D) if not a.out else rng.standard_normal((a.H, a.W))
     row0, rows = slab.partition(a.H, world, rank)
     eng = slab.CudaSlabEngine(a.W, a.H, row0, rows, local)
-    eng.upload(slab.with_ghosts(D, row0, rows), slab.with_ghosts(phi0, row0, rows))
-    slab.solve(eng, dist, rank, world, min(8, a.sweeps), 0.0, a.check_every)           # warm-up
-    eng.upload(slab.with_ghosts(D, row0, rows), slab.with_ghosts(phi0, row0, rows))
+    eng.upload(slab.with_ghosts(D, row0, rows, eng.GH), slab.with_ghosts(phi0, row0, rows, eng.GH))
+    slab.solve(eng, dist, rank, world, min(8, a.sweeps), 0.0, a.check_every, a.mode)           # warm-up
+    eng.upload(slab.with_ghosts(D, row0, rows, eng.GH), slab.with_ghosts(phi0, row0, rows, eng.GH))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    info = slab.solve(eng, dist, rank, world, a.sweeps, a.tol, a.check_every)
+    info = slab.solve(eng, dist, rank, world, a.sweeps, a.tol, a.check_every, a.mode)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -58,7 +59,7 @@ def main():
             np.savez(a.out, D=D, phi0=phi0, phi=np.concatenate(parts, axis=0))
     if rank == 0:
         us = float(ms.item()) * 1e3 / info["sweeps"]
-        print(json.dumps({"W": a.W, "H": a.H, "gpus": world, "sweeps": info["sweeps"], "us_per_sweep": us,
+        print(json.dumps({"W": a.W, "H": a.H, "gpus": world, "mode": info["mode"], "sweeps": info["sweeps"], "us_per_sweep": us,
                           "sweeps_per_s": 1e6 / us, "algorithmic_gbs": 24.0 * a.W * a.H / (us * 1e-6) / 1e9}), flush=True)
     eng.close()
     if world > 1:
