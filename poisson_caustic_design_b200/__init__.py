@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libpcd_b200.so")
+LIB_PATH = os.environ.get("PCD_LIB") or os.path.join(PKG_DIR, "libpcd_b200.so")  # PCD_LIB: diagnostic builds only
 
 PCD_OK, PCD_ERR_INVALID, PCD_ERR_CUDA, PCD_ERR_NO_DEVICE, PCD_ERR_RASTER_MISS, PCD_ERR_STATE, PCD_ERR_UNSUPPORTED = range(7)
 SOLVER_AUTO, SOLVER_STREAMING, SOLVER_RESIDENT, SOLVER_TILED = 0, 1, 2, 3
