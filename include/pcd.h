@@ -157,6 +157,7 @@ int pcd_solver_path_used(const pcd_solver *s);
 typedef struct pcd_slab pcd_slab;
 int pcd_slab_ghost_rows(void);
 int pcd_slab_sweeps_per_pass(void);
+void pcd_slab_set_sm_reserve(int n);   /* SMs the pass kernel leaves free for the collective's kernels (default 0) */
 int pcd_slab_create(int width, int height, int row0, int rows, int device, void *cuda_stream, pcd_slab **out);
 void pcd_slab_destroy(pcd_slab *s);
 int pcd_slab_device_ptrs(pcd_slab *s, void **phi0_dev, void **phi1_dev, void **sweep_max_dev);
@@ -166,6 +167,10 @@ int pcd_slab_upload(pcd_slab *s, const double *D_rows_with_ghosts, const double 
 int pcd_slab_download(pcd_slab *s, double *phi_owned_rows);
 int pcd_slab_sweep_colour(pcd_slab *s, int colour, int slot);
 int pcd_slab_pass(pcd_slab *s, int nsweeps, int slot);
+/* the same pass over owned rows [row_begin, row_begin+row_count) only, on cuda_stream (NULL = the slab's), without
+ * switching buffers; pcd_slab_flip switches them once every part has been issued (exchange/compute overlap) */
+int pcd_slab_pass_part(pcd_slab *s, int nsweeps, int slot, int row_begin, int row_count, void *cuda_stream);
+int pcd_slab_flip(pcd_slab *s);
 int pcd_slab_clear_max(pcd_slab *s, int n_slots);
 
 #ifdef __cplusplus

@@ -97,6 +97,9 @@ ABI = [
     ("pcd_slab_download", C.c_int, [C.c_void_p, _dp]),
     ("pcd_slab_sweep_colour", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("pcd_slab_pass", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("pcd_slab_pass_part", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("pcd_slab_flip", C.c_int, [C.c_void_p]),
+    ("pcd_slab_set_sm_reserve", None, [C.c_int]),
     ("pcd_slab_ghost_rows", C.c_int, []),
     ("pcd_slab_sweeps_per_pass", C.c_int, []),
     ("pcd_slab_current", C.c_int, [C.c_void_p]),

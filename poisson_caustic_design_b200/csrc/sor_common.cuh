@@ -45,6 +45,7 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
 
 // sor_tiled.cu
 int tiled_sweeps_per_pass();
+void tiled_set_sm_reserve(int n);  // SMs left free by the wavefront kernel (overlapped multi-GPU exchange)
 int tiled_pass(const double *phi_in, double *phi_out, const double *D, int W, int H, int row_first, int rows, int grow0,
                int nsweeps, unsigned long long *slots, cudaStream_t stream);
 

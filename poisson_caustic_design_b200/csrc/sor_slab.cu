@@ -85,6 +85,7 @@ extern "C" {
 
 int pcd_slab_ghost_rows(void) { return 2 * tiled_sweeps_per_pass() + 1; }
 int pcd_slab_sweeps_per_pass(void) { return tiled_sweeps_per_pass(); }
+void pcd_slab_set_sm_reserve(int n) { tiled_set_sm_reserve(n); }
 
 int pcd_slab_create(int width, int height, int row0, int rows, int device, void *cuda_stream, pcd_slab **out) {
     if (!out) { set_error("null argument"); return PCD_ERR_INVALID; }
@@ -195,6 +196,28 @@ int pcd_slab_pass(pcd_slab *s, int nsweeps, int slot) {
                        s->sweep_max + slot, s->stream));
     s->cur ^= 1;
     s->launches++;
+    return PCD_OK;
+}
+
+// The same pass restricted to owned rows [row_begin, row_begin+row_count) (global indices), on `cuda_stream` (NULL =
+// the slab's stream), WITHOUT switching buffers: the host layer runs the bands next to the slab edges first,
+// starts the ghost-row exchange on a side stream, runs the interior, then calls pcd_slab_flip.
+int pcd_slab_pass_part(pcd_slab *s, int nsweeps, int slot, int row_begin, int row_count, void *cuda_stream) {
+    if (!s || slot < 0 || slot + nsweeps > s->ring || nsweeps < 1 || nsweeps > tiled_sweeps_per_pass() ||
+        row_begin < s->row0 || row_count < 1 || row_begin + row_count > s->row0 + s->rows) {
+        set_error("bad slab / slot / sweep count / row range");
+        return PCD_ERR_INVALID;
+    }
+    if (s->has_nan) { set_error("pcd_slab_pass_part: D has NaN holes, use the colour path"); return PCD_ERR_UNSUPPORTED; }
+    PCD_TRY(tiled_pass(s->phi[s->cur], s->phi[s->cur ^ 1], s->D, s->W, s->H, row_begin, row_count, s->row0 - s->GH, nsweeps,
+                       s->sweep_max + slot, cuda_stream ? (cudaStream_t)cuda_stream : s->stream));
+    s->launches++;
+    return PCD_OK;
+}
+
+int pcd_slab_flip(pcd_slab *s) {
+    if (!s) { set_error("null slab"); return PCD_ERR_INVALID; }
+    s->cur ^= 1;
     return PCD_OK;
 }
 

@@ -247,6 +247,8 @@ __global__ void __launch_bounds__(WAVE_NT, 2) sor_wave_kernel(const __grid_const
 
 constexpr int TILED_TS = 2;
 int tiled_sweeps_per_pass() { return TILED_TS; }
+static int g_sm_reserve = 0;
+void tiled_set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : n; }
 
 template <int TS>
 static int launch_wave(const WaveParams &prm, int sm_count, cudaStream_t stream) {
@@ -261,7 +263,9 @@ static int launch_wave(const WaveParams &prm, int sm_count, cudaStream_t stream)
     const int strips = (p.W + Cfg::CORE - 1) / Cfg::CORE;
     // ONE wave of two CTAs per SM (never a second, nearly empty wave); chunks long enough that the 2*NP warm-up
     // rows stay a small fraction
-    int chunks = (2 * sm_count) / strips;
+    // (multi-GPU runs keep a few SMs free so that the NCCL kernels of the overlapped ghost-row exchange can run)
+    const int avail = (sm_count - g_sm_reserve >= 8) ? sm_count - g_sm_reserve : sm_count;
+    int chunks = (2 * avail) / strips;
     const int min_rows = 16 * Cfg::NP;
     if (chunks * min_rows > p.rows) chunks = p.rows / min_rows;
     if (chunks < 1) chunks = 1;

@@ -88,6 +88,22 @@ class CudaSlabEngine:
     def pass_(self, nsweeps: int, slot: int):
         _check(lib().pcd_slab_pass(self._h, nsweeps, slot))
 
+    def pass_part(self, nsweeps: int, slot: int, row_begin: int, row_count: int, stream=None):
+        """The pass over owned rows [row_begin, row_begin+row_count) only (global indices); buffers are not switched."""
+        cs = C.c_void_p(stream.cuda_stream) if stream is not None else None
+        _check(lib().pcd_slab_pass_part(self._h, nsweeps, slot, row_begin, row_count, cs))
+
+    def flip(self):
+        _check(lib().pcd_slab_flip(self._h))
+
+    def bands(self, band: int = 64):
+        """(edge bands, interior) row ranges of a pass: the bands produce everything the neighbours need."""
+        r0, n = self.row0, self.rows
+        b = min(band, n // 2)
+        if b < self.GH or n - 2 * b < 1:
+            return [(r0, n)], None
+        return [(r0, b), (r0 + n - b, b)], (r0 + b, n - 2 * b)
+
     def clear_max(self, n: int):
         _check(lib().pcd_slab_clear_max(self._h, n))
 
@@ -143,11 +159,35 @@ def solve(engine, dist, rank: int, world: int, max_iterations: int, tol: float, 
     TS = engine.TS if wave else 1
     check_every = max(TS, min(check_every, 4096))
     check_every = (check_every + TS - 1) // TS * TS
+    # exchange/compute overlap (CUDA engines, world > 1): the bands next to the slab edges run first, their ghost-row
+    # exchange goes to a side stream while the interior rows of the same pass are still being updated
+    overlap = wave and world > 1 and hasattr(engine, "pass_part") and engine.bands()[1] is not None
+    if overlap:
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        ev_bands, ev_xchg = torch.cuda.Event(), torch.cuda.Event()
+        edge_bands, interior = engine.bands()
+        lib().pcd_slab_set_sm_reserve(8)   # room for the NCCL send/recv kernels next to the interior pass
     done, conv, last = 0, 0, 0.0
     while done < max_iterations and not conv:
         k = min(check_every, max_iterations - done)
         engine.clear_max(k)
-        if wave:
+        if wave and overlap:
+            j = 0
+            while j < k:
+                ns = min(TS, k - j)
+                for (rb, rc) in edge_bands:
+                    engine.pass_part(ns, j, rb, rc)
+                ev_bands.record(main)
+                engine.pass_part(ns, j, interior[0], interior[1])
+                engine.flip()
+                with torch.cuda.stream(side):
+                    side.wait_event(ev_bands)
+                    _exchange(engine, dist, rank, world, engine.GH)   # on the buffer the pass just filled
+                    ev_xchg.record(side)
+                main.wait_event(ev_xchg)
+                j += ns
+        elif wave:
             j = 0
             while j < k:
                 ns = min(TS, k - j)
@@ -200,7 +240,14 @@ def solve_local(engines, max_iterations: int, tol: float, check_every: int = 64,
             while j < k:
                 ns = min(TS, k - j)
                 for e in engines:
-                    e.pass_(ns, j)
+                    if hasattr(e, "pass_part") and e.bands()[1] is not None:   # same banded pass as the overlapped path
+                        eb, inner = e.bands()
+                        for (rb, rc) in eb:
+                            e.pass_part(ns, j, rb, rc)
+                        e.pass_part(ns, j, inner[0], inner[1])
+                        e.flip()
+                    else:
+                        e.pass_(ns, j)
                 exchange(e0.GH)
                 j += ns
         else:
