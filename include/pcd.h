@@ -172,6 +172,19 @@ int pcd_slab_pass(pcd_slab *s, int nsweeps, int slot);
 int pcd_slab_pass_part(pcd_slab *s, int nsweeps, int slot, int row_begin, int row_count, void *cuda_stream);
 int pcd_slab_flip(pcd_slab *s);
 int pcd_slab_clear_max(pcd_slab *s, int n_slots);
+/* Ghost-row exchange FUSED into the pass (no host-side collective on the data path): the kernel stores the
+ * pcd_slab_ghost_rows() rows next to a slab edge straight into the neighbour's field (peer memory over NVLink)
+ * and raises a sequence flag there; the neighbour's next pass waits for that flag on the device.  Neighbours are
+ * attached once: across processes through CUDA IPC handles (export -> send with torch.distributed -> connect),
+ * inside one process directly.  side 0 = the slab owning the rows above, 1 = the rows below.  All ranks issue
+ * the same sequence of pcd_slab_peer_run calls; pcd_slab_peer_status waits for the stream and reports whether a
+ * pass ran into the 3 s limit waiting for a neighbour. */
+int pcd_slab_peer_handle_bytes(void);
+int pcd_slab_peer_export(pcd_slab *s, unsigned char *handles);
+int pcd_slab_peer_connect_ipc(pcd_slab *s, int side, const unsigned char *handles, int peer_row0, int peer_rows);
+int pcd_slab_peer_connect_local(pcd_slab *s, int side, pcd_slab *peer);
+int pcd_slab_peer_run(pcd_slab *s, int nsweeps, int slot);
+int pcd_slab_peer_status(pcd_slab *s, int *timed_out);
 
 #ifdef __cplusplus
 }

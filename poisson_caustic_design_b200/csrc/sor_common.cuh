@@ -49,4 +49,21 @@ void tiled_set_sm_reserve(int n);  // SMs left free by the wavefront kernel (ove
 int tiled_pass(const double *phi_in, double *phi_out, const double *D, int W, int H, int row_first, int rows, int grow0,
                int nsweeps, unsigned long long *slots, cudaStream_t stream);
 
+// Ghost-row exchange fused into the wavefront pass (multi-GPU slabs): the CTAs that finish the `gh` owned rows next to
+// a slab edge store them to the neighbour's output field as well (peer memory over NVLink) and the last of them
+// raises the neighbour's flag to `seq`; the CTAs that read ghost rows first wait until their flag reached seq-1.
+struct WavePeer {
+    double *up_out = nullptr, *dn_out = nullptr;  // neighbours' phi_out arrays (local row 0 = global row *_grow0)
+    int up_grow0 = 0, dn_grow0 = 0;
+    int gh = 0;
+    const unsigned *wait_up = nullptr, *wait_dn = nullptr;  // local flags, written by the neighbours
+    unsigned *sig_up = nullptr, *sig_dn = nullptr;           // the neighbours' flags
+    unsigned *cnt = nullptr;                                  // local arrival counters [2]
+    int *err = nullptr;                                       // local: set when a wait ran into its time limit
+    unsigned seq = 0;                                         // sequence number of this pass (first pass: 1)
+    int tail_rows = 0;                                        // rows of the short last chunk (filled by the launcher)
+};
+int tiled_pass_peer(const double *phi_in, double *phi_out, const double *D, int W, int H, int row_first, int rows, int grow0,
+                    int nsweeps, unsigned long long *slots, const WavePeer &peer, cudaStream_t stream);
+
 }  // namespace pcd

@@ -9,7 +9,11 @@
 // The host layer (slab.py, torch.distributed: NCCL over NVLink, gloo in CPU tests) does the exchanges and
 // all-reduces the per-sweep max.  Per-cell arithmetic is the single-GPU kernels', so a G-slab solve is
 // bit-identical to the single-GPU solve (red-black updates of one colour are order-independent, max is exact).
+#include <cstring>
+
 #include "sor_common.cuh"
+
+constexpr size_t PCD_SLAB_CTL_BYTES = 256;
 
 struct pcd_slab {
     int W = 0, H = 0, row0 = 0, rows = 0, device = 0, GH = 0;
@@ -23,6 +27,13 @@ struct pcd_slab {
     int has_nan = 0;
     int ring = 0;
     long long launches = 0;
+    // fused peer exchange (pcd_slab_peer_*): control words live behind phi[0] so that one IPC handle covers them
+    unsigned *ctl = nullptr;              // [0],[1]: flags raised by the upper / lower neighbour; [4],[5]: arrival counters; [8]: error
+    double *peer_phi[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [side][buffer], side 0 = up, 1 = down
+    unsigned *peer_ctl[2] = {nullptr, nullptr};
+    int peer_row0[2] = {0, 0};
+    bool peer_ipc[2] = {false, false};
+    unsigned seq = 0;
 };
 
 namespace pcd {
@@ -101,13 +112,13 @@ int pcd_slab_create(int width, int height, int row0, int rows, int device, void 
     s->stream = (cudaStream_t)cuda_stream;
     s->ring = 4096;
     const size_t n = (size_t)(rows + 2 * s->GH) * width;
-    cudaError_t e = cudaMalloc(&s->phi[0], n * sizeof(double));
+    cudaError_t e = cudaMalloc(&s->phi[0], n * sizeof(double) + PCD_SLAB_CTL_BYTES);
     if (e == cudaSuccess) e = cudaMalloc(&s->phi[1], n * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&s->D, n * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&s->mask, n);
     if (e == cudaSuccess) e = cudaMalloc(&s->sweep_max, sizeof(unsigned long long) * s->ring);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_flag, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(s->phi[0], 0, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(s->phi[0], 0, n * sizeof(double) + PCD_SLAB_CTL_BYTES);
     if (e == cudaSuccess) e = cudaMemset(s->phi[1], 0, n * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(s->D, 0, n * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(s->mask, 0, n);
@@ -119,6 +130,7 @@ int pcd_slab_create(int width, int height, int row0, int rows, int device, void 
         delete s;
         return PCD_ERR_CUDA;
     }
+    s->ctl = reinterpret_cast<unsigned *>(s->phi[0] + n);
     *out = s;
     return PCD_OK;
 }
@@ -126,6 +138,11 @@ int pcd_slab_create(int width, int height, int row0, int rows, int device, void 
 void pcd_slab_destroy(pcd_slab *s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    for (int side = 0; side < 2; ++side)
+        if (s->peer_ipc[side]) {
+            cudaIpcCloseMemHandle(s->peer_phi[side][0]);
+            cudaIpcCloseMemHandle(s->peer_phi[side][1]);
+        }
     cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->D); cudaFree(s->mask); cudaFree(s->sweep_max); cudaFree(s->d_flag);
     delete s;
 }
@@ -218,6 +235,101 @@ int pcd_slab_pass_part(pcd_slab *s, int nsweeps, int slot, int row_begin, int ro
 int pcd_slab_flip(pcd_slab *s) {
     if (!s) { set_error("null slab"); return PCD_ERR_INVALID; }
     s->cur ^= 1;
+    return PCD_OK;
+}
+
+// ---- ghost-row exchange fused into the pass (peer memory over NVLink; see WavePeer in sor_common.cuh) ----
+
+int pcd_slab_peer_handle_bytes(void) { return 2 * (int)sizeof(cudaIpcMemHandle_t); }
+
+// IPC handles of the two field buffers (the control words sit behind buffer 0) for the neighbouring processes
+int pcd_slab_peer_export(pcd_slab *s, unsigned char *handles) {
+    if (!s || !handles) { set_error("null argument"); return PCD_ERR_INVALID; }
+    PCD_TRY(select_device(s->device));
+    cudaIpcMemHandle_t h[2];
+    PCD_CUDA(cudaIpcGetMemHandle(&h[0], s->phi[0]));
+    PCD_CUDA(cudaIpcGetMemHandle(&h[1], s->phi[1]));
+    memcpy(handles, h, sizeof(h));
+    return PCD_OK;
+}
+
+static int peer_attach(pcd_slab *s, int side, double *phi0, double *phi1, int peer_row0, int peer_rows, bool ipc) {
+    const int expect = side == 0 ? s->row0 - peer_rows : s->row0 + s->rows;
+    if (peer_row0 != expect || peer_rows < 2 * s->GH || s->rows < 2 * s->GH) {
+        set_error("pcd_slab_peer_connect: rows [%d,%d) are not the %s neighbour of [%d,%d), or a slab is thinner than %d rows",
+                  peer_row0, peer_row0 + peer_rows, side == 0 ? "upper" : "lower", s->row0, s->row0 + s->rows, 2 * s->GH);
+        return PCD_ERR_INVALID;
+    }
+    s->peer_phi[side][0] = phi0;
+    s->peer_phi[side][1] = phi1;
+    s->peer_ctl[side] = reinterpret_cast<unsigned *>(phi0 + (size_t)(peer_rows + 2 * s->GH) * s->W);
+    s->peer_row0[side] = peer_row0;
+    s->peer_ipc[side] = ipc;
+    return PCD_OK;
+}
+
+// side 0: the slab that owns the rows above, side 1: the rows below.  `handles` from pcd_slab_peer_export in the
+// neighbour's process.
+int pcd_slab_peer_connect_ipc(pcd_slab *s, int side, const unsigned char *handles, int peer_row0, int peer_rows) {
+    if (!s || !handles || side < 0 || side > 1 || s->peer_phi[side][0]) { set_error("bad slab / side / handles"); return PCD_ERR_INVALID; }
+    PCD_TRY(select_device(s->device));
+    cudaIpcMemHandle_t h[2];
+    memcpy(h, handles, sizeof(h));
+    void *p0 = nullptr, *p1 = nullptr;
+    PCD_CUDA(cudaIpcOpenMemHandle(&p0, h[0], cudaIpcMemLazyEnablePeerAccess));
+    cudaError_t e = cudaIpcOpenMemHandle(&p1, h[1], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaIpcCloseMemHandle(p0);
+        set_error("cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+        return PCD_ERR_CUDA;
+    }
+    const int rc = peer_attach(s, side, (double *)p0, (double *)p1, peer_row0, peer_rows, true);
+    if (rc != PCD_OK) { cudaIpcCloseMemHandle(p0); cudaIpcCloseMemHandle(p1); }
+    return rc;
+}
+
+// the neighbour lives in this process on the same device (several slabs per GPU; single-GPU tests of the fused path)
+int pcd_slab_peer_connect_local(pcd_slab *s, int side, pcd_slab *peer) {
+    if (!s || !peer || side < 0 || side > 1 || peer->device != s->device || peer->W != s->W) { set_error("bad slab / side / peer"); return PCD_ERR_INVALID; }
+    return peer_attach(s, side, peer->phi[0], peer->phi[1], peer->row0, peer->rows, false);
+}
+
+// nsweeps sweeps as ceil(nsweeps / TS) fused passes, maxima into slots [slot, slot+nsweeps).  Asynchronous; nothing
+// but kernel launches on the slab's stream.  Every rank must issue the same sequence of peer runs.
+int pcd_slab_peer_run(pcd_slab *s, int nsweeps, int slot) {
+    if (!s || slot < 0 || nsweeps < 1 || slot + nsweeps > s->ring) { set_error("bad slab / slot / sweep count"); return PCD_ERR_INVALID; }
+    if (s->has_nan) { set_error("pcd_slab_peer_run: D has NaN holes, use the colour path"); return PCD_ERR_UNSUPPORTED; }
+    const int TS = tiled_sweeps_per_pass();
+    for (int j = 0; j < nsweeps; j += TS) {
+        const int ns = nsweeps - j < TS ? nsweeps - j : TS;
+        const int o = s->cur ^ 1;
+        WavePeer pr;
+        pr.gh = s->GH;
+        pr.cnt = s->ctl + 4;
+        pr.err = reinterpret_cast<int *>(s->ctl + 8);
+        pr.seq = ++s->seq;
+        if (s->peer_phi[0][0]) {
+            pr.up_out = s->peer_phi[0][o]; pr.up_grow0 = s->peer_row0[0] - s->GH;
+            pr.wait_up = s->ctl + 0; pr.sig_up = s->peer_ctl[0] + 1;   // I am its lower neighbour
+        }
+        if (s->peer_phi[1][0]) {
+            pr.dn_out = s->peer_phi[1][o]; pr.dn_grow0 = s->peer_row0[1] - s->GH;
+            pr.wait_dn = s->ctl + 1; pr.sig_dn = s->peer_ctl[1] + 0;   // I am its upper neighbour
+        }
+        PCD_TRY(tiled_pass_peer(s->phi[s->cur], s->phi[o], s->D, s->W, s->H, s->row0, s->rows, s->row0 - s->GH, ns,
+                                s->sweep_max + slot + j, pr, s->stream));
+        s->cur = o;
+        s->launches++;
+    }
+    return PCD_OK;
+}
+
+// waits for the slab's stream; *timed_out = 1 when a pass gave up waiting for a neighbour (results are then invalid)
+int pcd_slab_peer_status(pcd_slab *s, int *timed_out) {
+    if (!s || !timed_out) { set_error("null argument"); return PCD_ERR_INVALID; }
+    PCD_TRY(select_device(s->device));
+    PCD_CUDA(cudaMemcpyAsync(timed_out, s->ctl + 8, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    PCD_CUDA(cudaStreamSynchronize(s->stream));
     return PCD_OK;
 }
 

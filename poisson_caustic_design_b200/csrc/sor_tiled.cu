@@ -20,6 +20,8 @@
 // masked colour kernels when D contains NaN).
 #include <cuda_pipeline_primitives.h>
 
+#include <cstdlib>
+
 #include "sor_common.cuh"
 
 namespace pcd {
@@ -44,10 +46,43 @@ struct WaveParams {
     int W, H;            // global grid
     int row_first, rows; // owned global rows [row_first, row_first + rows)
     int grow0;           // global row of local row 0 of the arrays
-    int chunk_rows;
+    int nchunks;         // row chunks (not counting the short last chunk of a PEER pass)
     SorW w;
     unsigned long long *slots;  // per-sweep max, TS entries used
+    WavePeer peer;              // fused ghost-row exchange (PEER kernels only)
 };
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// thread 0 of a CTA that is about to read ghost rows: wait until the neighbour's pass `want` has delivered them
+__device__ __forceinline__ void peer_wait(const unsigned *flag, unsigned want, int *err) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - want) < 0) {
+        if (clock64() - t0 > 6000000000ll) {  // ~3 s: a neighbour died; report instead of hanging the GPU
+            atomicExch(err, 1);
+            break;
+        }
+        __nanosleep(64);
+    }
+}
+// all threads of the CTA: the edge rows of this CTA are stored; the last of the n_ctas CTAs raises the neighbour's flag
+__device__ __forceinline__ void peer_signal(unsigned *cnt, unsigned *sig, unsigned seq, unsigned n_ctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(cnt, 1u) == n_ctas - 1) {
+            atomicExch(cnt, 0u);
+            __threadfence_system();
+            st_release_sys(sig, seq);
+        }
+    }
+}
 
 struct WaveThread {  // per-thread invariants
     int k, gx0;
@@ -58,7 +93,7 @@ struct WaveThread {  // per-thread invariants
 
 // One row step.  C = (f - ys) mod R is compile-time; chunks start so that the active cell of row r in phase ph
 // has window parity (r - ys + 1 + ph) & 1, i.e. (C + ph) & 1 for the row f-1-2ph updated at offset C.
-template <int TS, int C, bool STEADY>
+template <int TS, int C, bool STEADY, bool PEER>
 __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveThread &t, const int f,
                                           double (&v)[WaveCfg<TS>::R][2], double *__restrict__ sphi,
                                           double *__restrict__ sD, double (&lmax)[TS]) {
@@ -143,6 +178,15 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveThread 
                 if (t.ex0) p.phi_out[o] = v[SL][0];
                 if (t.ex1) p.phi_out[o + 1] = v[SL][1];
             }
+            if constexpr (PEER && !STEADY) {  // rows next to a slab edge also go to the neighbour's ghost rows
+                double *dst = nullptr;
+                if (p.peer.up_out && r < p.row_first + p.peer.gh) dst = p.peer.up_out + (size_t)(r - p.peer.up_grow0) * W + t.gx0;
+                if (p.peer.dn_out && r >= p.row_first + p.rows - p.peer.gh) dst = p.peer.dn_out + (size_t)(r - p.peer.dn_grow0) * W + t.gx0;
+                if (dst) {
+                    if (t.ex0) dst[0] = v[SL][0];
+                    if (t.ex1) dst[1] = v[SL][1];
+                }
+            }
         }
     }
     // (e) row f+1 must have landed before the next step reads it
@@ -150,16 +194,17 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveThread 
     __syncthreads();
 }
 
-template <int TS, int C, bool STEADY>
+template <int TS, int C, bool STEADY, bool PEER>
 struct WaveUnroll {
-    static __device__ __forceinline__ void run(const WaveParams &p, const WaveThread &t, const int f,
+    static __device__ __forceinline__ void run(const WaveParams &p, const WaveThread &t, const int f, const int f_last,
                                                double (&v)[WaveCfg<TS>::R][2], double *sphi, double *sD, double (&lmax)[TS]) {
-        wave_step<TS, C, STEADY>(p, t, f + C, v, sphi, sD, lmax);
-        if constexpr (C + 1 < WaveCfg<TS>::R) WaveUnroll<TS, C + 1, STEADY>::run(p, t, f, v, sphi, sD, lmax);
+        if (!STEADY && f + C > f_last) return;  // CTA-uniform: the chunk's last block stops at its last step
+        wave_step<TS, C, STEADY, PEER>(p, t, f + C, v, sphi, sD, lmax);
+        if constexpr (C + 1 < WaveCfg<TS>::R) WaveUnroll<TS, C + 1, STEADY, PEER>::run(p, t, f, f_last, v, sphi, sD, lmax);
     }
 };
 
-template <int TS>
+template <int TS, bool PEER>
 __global__ void __launch_bounds__(WAVE_NT, 2) sor_wave_kernel(const __grid_constant__ WaveParams p) {
     using Cfg = WaveCfg<TS>;
     constexpr int R = Cfg::R, NP = Cfg::NP, PITCH = Cfg::PITCH;
@@ -172,9 +217,23 @@ __global__ void __launch_bounds__(WAVE_NT, 2) sor_wave_kernel(const __grid_const
     t.k = threadIdx.x;
     const int W = p.W, H = p.H;
     const int xw0 = blockIdx.x * Cfg::CORE - Cfg::HX;              // window origin (global x, even)
-    t.y0 = p.row_first + blockIdx.y * p.chunk_rows;
-    t.y1 = min(t.y0 + p.chunk_rows, p.row_first + p.rows);
+    if (PEER && p.peer.tail_rows > 0 && blockIdx.y == gridDim.y - 1) {  // short last chunk: the bottom edge rows leave early
+        t.y1 = p.row_first + p.rows;
+        t.y0 = t.y1 - p.peer.tail_rows;
+    } else {
+        const int main_rows = p.rows - (PEER ? p.peer.tail_rows : 0);   // balanced split: chunk lengths differ by <= 1 row
+        t.y0 = p.row_first + (int)blockIdx.y * main_rows / p.nchunks;
+        t.y1 = p.row_first + ((int)blockIdx.y + 1) * main_rows / p.nchunks;
+    }
     if (t.y0 >= t.y1) return;
+    const bool top = PEER && t.y0 == p.row_first && p.peer.up_out != nullptr;
+    const bool bot = PEER && t.y1 == p.row_first + p.rows && p.peer.dn_out != nullptr;
+    if constexpr (PEER) {
+        if (threadIdx.x == 0) {
+            if (top) peer_wait(p.peer.wait_up, p.peer.seq - 1, p.peer.err);
+            if (bot) peer_wait(p.peer.wait_dn, p.peer.seq - 1, p.peer.err);
+        }
+    }
     // first row streamed in: NP rows of warm-up, moved one row earlier when needed so that the colour parity of
     // every (step offset, phase) pair is a compile-time constant: active parity of row r in phase ph is
     // (xw0 + r + ph) & 1 = (r + ph) & 1, and r = ys + C - 1 - 2ph at offset C  =>  need ys odd
@@ -218,13 +277,28 @@ __global__ void __launch_bounds__(WAVE_NT, 2) sor_wave_kernel(const __grid_const
     __syncthreads();
 
     const int f_last = t.y1 + 2 * (NP - 1);
+    bool up_sent = false;
     for (int fb = t.ys; fb <= f_last; fb += R) {
         // a block of R steps is steady when every row any phase touches is owned and not a domain edge row, and
         // every row streamed in exists
         const int r_min = fb - 1 - 2 * (NP - 1), r_max = fb + R - 2, f_max = fb + R - 1 + WAVE_PF;
-        const bool steady = r_min >= max(t.y0, 1) && r_max <= min(t.y1 - 1, H - 2) && f_max <= min(t.ye, H - 1);
-        if (steady) WaveUnroll<TS, 0, true>::run(p, t, fb, v, sphi, sD, lmax);
-        else WaveUnroll<TS, 0, false>::run(p, t, fb, v, sphi, sD, lmax);
+        bool steady = r_min >= max(t.y0, 1) && r_max <= min(t.y1 - 1, H - 2) && f_max <= min(t.ye, H - 1);
+        if constexpr (PEER) {  // rows stored by this block: r_min .. r_min + R - 1; edge rows take the checked variant
+            if (top && r_min < p.row_first + p.peer.gh) steady = false;
+            if (bot && r_min + R - 1 >= p.row_first + p.rows - p.peer.gh) steady = false;
+        }
+        if (steady) WaveUnroll<TS, 0, true, PEER>::run(p, t, fb, f_last, v, sphi, sD, lmax);
+        else WaveUnroll<TS, 0, false, PEER>::run(p, t, fb, f_last, v, sphi, sD, lmax);
+        if constexpr (PEER) {  // the top edge rows are complete long before the chunk is: tell the upper neighbour now
+            if (top && !up_sent && r_min + R - 1 >= p.row_first + p.peer.gh - 1) {
+                peer_signal(p.peer.cnt, p.peer.sig_up, p.peer.seq, gridDim.x);
+                up_sent = true;
+            }
+        }
+    }
+    if constexpr (PEER) {
+        if (top && !up_sent) peer_signal(p.peer.cnt, p.peer.sig_up, p.peer.seq, gridDim.x);
+        if (bot) peer_signal(p.peer.cnt + 1, p.peer.sig_dn, p.peer.seq, gridDim.x);
     }
 
     // publish the per-sweep maxima
@@ -250,28 +324,38 @@ int tiled_sweeps_per_pass() { return TILED_TS; }
 static int g_sm_reserve = 0;
 void tiled_set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : n; }
 
-template <int TS>
+template <int TS, bool PEER>
 static int launch_wave(const WaveParams &prm, int sm_count, cudaStream_t stream) {
     using Cfg = WaveCfg<TS>;
     static bool attr_set = false;
     const size_t smem = (size_t)2 * Cfg::R * 2 * Cfg::PITCH * sizeof(double);
     if (!attr_set) {
-        PCD_CUDA(cudaFuncSetAttribute(sor_wave_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PCD_CUDA(cudaFuncSetAttribute(sor_wave_kernel<TS, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     WaveParams p = prm;
     const int strips = (p.W + Cfg::CORE - 1) / Cfg::CORE;
-    // ONE wave of two CTAs per SM (never a second, nearly empty wave); chunks long enough that the 2*NP warm-up
-    // rows stay a small fraction
+    // ONE wave of two CTAs per SM (never a second, nearly empty wave).  Measured on B200 (2048^2: 59 chunks of 35
+    // rows 19.8 us/sweep, 32 chunks of 64 rows 28.6): the row step is latency-bound, so the shortest chunks that
+    // still fit one wave win even though the 2*NP warm-up rows are then a larger share of the work
     // (multi-GPU runs keep a few SMs free so that the NCCL kernels of the overlapped ghost-row exchange can run)
     const int avail = (sm_count - g_sm_reserve >= 8) ? sm_count - g_sm_reserve : sm_count;
     int chunks = (2 * avail) / strips;
-    const int min_rows = 16 * Cfg::NP;
-    if (chunks * min_rows > p.rows) chunks = p.rows / min_rows;
+    int min_rows = 4 * Cfg::NP;  // a step costs the same latency whatever the chunk length: fill the wave first
+    static const int dbg_chunks = getenv("PCD_WAVE_CHUNKS") ? atoi(getenv("PCD_WAVE_CHUNKS")) : 0;  // tuning knob
+    if (dbg_chunks > 0) { chunks = dbg_chunks; min_rows = 8; }
+    int tail = 0;
+    if constexpr (PEER) {
+        // with a lower neighbour the bottom rows get a short chunk of their own (they are the LAST rows a chunk
+        // walking down would finish), so that the neighbour has them long before the pass ends
+        if (p.peer.dn_out && p.rows >= 8 * min_rows && chunks >= 3) { tail = 2 * Cfg::NP + 4; chunks -= 1; }
+        p.peer.tail_rows = tail;
+    }
+    const int main_rows = p.rows - tail;
+    if (chunks * min_rows > main_rows) chunks = main_rows / min_rows;
     if (chunks < 1) chunks = 1;
-    p.chunk_rows = (p.rows + chunks - 1) / chunks;
-    chunks = (p.rows + p.chunk_rows - 1) / p.chunk_rows;
-    sor_wave_kernel<TS><<<dim3(strips, chunks), WAVE_NT, smem, stream>>>(p);
+    p.nchunks = chunks;
+    sor_wave_kernel<TS, PEER><<<dim3(strips, chunks + (tail ? 1 : 0)), WAVE_NT, smem, stream>>>(p);
     PCD_LAUNCHED();
     return PCD_OK;
 }
@@ -289,10 +373,27 @@ int tiled_pass(const double *phi_in, double *phi_out, const double *D, int W, in
     }
     WaveParams prm;
     prm.phi_in = phi_in; prm.phi_out = phi_out; prm.D = D; prm.W = W; prm.H = H;
-    prm.row_first = row_first; prm.rows = rows; prm.grow0 = grow0; prm.chunk_rows = rows;
+    prm.row_first = row_first; prm.rows = rows; prm.grow0 = grow0; prm.nchunks = 1;
     prm.w = make_w(W); prm.slots = slots;
-    if (nsweeps >= 2) return launch_wave<2>(prm, sm_count, stream);
-    return launch_wave<1>(prm, sm_count, stream);
+    if (nsweeps >= 2) return launch_wave<2, false>(prm, sm_count, stream);
+    return launch_wave<1, false>(prm, sm_count, stream);
+}
+
+// The same pass over a whole slab with the ghost-row exchange fused in (see WavePeer).
+int tiled_pass_peer(const double *phi_in, double *phi_out, const double *D, int W, int H, int row_first, int rows, int grow0,
+                    int nsweeps, unsigned long long *slots, const WavePeer &peer, cudaStream_t stream) {
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        PCD_CUDA(cudaGetDevice(&dev));
+        PCD_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    WaveParams prm;
+    prm.phi_in = phi_in; prm.phi_out = phi_out; prm.D = D; prm.W = W; prm.H = H;
+    prm.row_first = row_first; prm.rows = rows; prm.grow0 = grow0; prm.nchunks = 1;
+    prm.w = make_w(W); prm.slots = slots; prm.peer = peer;
+    if (nsweeps >= 2) return launch_wave<2, true>(prm, sm_count, stream);
+    return launch_wave<1, true>(prm, sm_count, stream);
 }
 
 }  // namespace pcd

@@ -80,7 +80,8 @@ class CudaSlabEngine:
         return bool(lib().pcd_slab_has_nan(self._h))
 
     def upload(self, D_g: np.ndarray, phi_g: np.ndarray):
-        _check(lib().pcd_slab_upload(self._h, _p(np.ascontiguousarray(D_g)), _p(np.ascontiguousarray(phi_g))))
+        _check(lib().pcd_slab_upload(self._h, None if D_g is None else _p(np.ascontiguousarray(D_g)),
+                                     None if phi_g is None else _p(np.ascontiguousarray(phi_g))))
 
     def sweep_colour(self, colour: int, slot: int):
         _check(lib().pcd_slab_sweep_colour(self._h, colour, slot))
@@ -103,6 +104,27 @@ class CudaSlabEngine:
         if b < self.GH or n - 2 * b < 1:
             return [(r0, n)], None
         return [(r0, b), (r0 + n - b, b)], (r0 + b, n - 2 * b)
+
+    # ---- ghost-row exchange fused into the pass kernel (peer memory over NVLink) ----
+    def peer_export(self) -> np.ndarray:
+        h = np.zeros(lib().pcd_slab_peer_handle_bytes(), dtype=np.uint8)
+        _check(lib().pcd_slab_peer_export(self._h, h.ctypes.data_as(C.c_void_p)))
+        return h
+
+    def peer_connect_ipc(self, side: int, handles: np.ndarray, peer_row0: int, peer_rows: int):
+        h = np.ascontiguousarray(handles, dtype=np.uint8)
+        _check(lib().pcd_slab_peer_connect_ipc(self._h, side, h.ctypes.data_as(C.c_void_p), peer_row0, peer_rows))
+
+    def peer_connect_local(self, side: int, other: "CudaSlabEngine"):
+        _check(lib().pcd_slab_peer_connect_local(self._h, side, other._h))
+
+    def peer_run(self, nsweeps: int, slot: int):
+        _check(lib().pcd_slab_peer_run(self._h, nsweeps, slot))
+
+    def peer_timed_out(self) -> bool:
+        t = C.c_int(0)
+        _check(lib().pcd_slab_peer_status(self._h, C.byref(t)))
+        return bool(t.value)
 
     def clear_max(self, n: int):
         _check(lib().pcd_slab_clear_max(self._h, n))
@@ -150,12 +172,51 @@ def use_wavefront(engine, dist, world: int, min_rows: int) -> bool:
     return bool(ok)
 
 
+def connect_peers(engine, dist, rank: int, world: int) -> bool:
+    """Attach the neighbouring ranks' slabs for the fused exchange (CUDA IPC handles travel through an all-gather).
+    Same answer on every rank; False leaves the host-driven exchange in charge."""
+    import torch
+    if getattr(engine, "_peers_connected", False):
+        return True
+    if not hasattr(engine, "peer_run"):   # engine type is the same on every rank
+        return False
+    H = engine.H
+    min_rows = min(partition(H, world, r)[1] for r in range(world))
+    ok = int(hasattr(engine, "peer_run") and world > 1 and min_rows >= 2 * engine.GH)
+    dev = engine.phi.device
+    mine = torch.from_numpy(engine.peer_export()).to(dev) if ok else torch.zeros(128, dtype=torch.uint8, device=dev)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    if ok:
+        try:
+            for side, nb in ((0, rank - 1), (1, rank + 1)):
+                if 0 <= nb < world:
+                    r0, n = partition(H, world, nb)
+                    engine.peer_connect_ipc(side, gathered[nb].cpu().numpy(), r0, n)
+        except RuntimeError:
+            ok = 0
+    t = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    engine._peers_connected = bool(t.item())
+    return engine._peers_connected
+
+
 def solve(engine, dist, rank: int, world: int, max_iterations: int, tol: float, check_every: int = 64, mode: str = "auto"):
-    """Distributed red-black SOR.  Returns {"sweeps", "converged_at", "last_max_update", "mode"} (same on all ranks)."""
+    """Distributed red-black SOR.  Returns {"sweeps", "converged_at", "last_max_update", "mode"} (same on all ranks).
+
+    mode: "auto" (fused peer exchange when the neighbours' memory can be attached, else wavefront passes with a
+    host-driven exchange, else colour phases), "peer", "wavefront", "colour"."""
     import torch
     H = engine.H
     min_rows = min(partition(H, world, r)[1] for r in range(world))
-    wave = use_wavefront(engine, dist, world, min_rows) if mode == "auto" else (mode == "wavefront")
+    wave = use_wavefront(engine, dist, world, min_rows) if mode in ("auto", "peer") else (mode == "wavefront")
+    peer = False
+    if wave and world > 1 and mode in ("auto", "peer"):
+        peer = connect_peers(engine, dist, rank, world)
+        if mode == "peer" and not peer:
+            raise RuntimeError("slab.solve(mode='peer'): the neighbouring slabs could not be attached")
+    if peer:
+        return _solve_peer(engine, dist, world, max_iterations, tol, check_every)
     TS = engine.TS if wave else 1
     check_every = max(TS, min(check_every, 4096))
     check_every = (check_every + TS - 1) // TS * TS
@@ -208,6 +269,53 @@ def solve(engine, dist, rank: int, world: int, max_iterations: int, tol: float, 
         conv, last = _decide(m_host, tol, done)
         done += k
     return {"sweeps": done, "converged_at": conv, "last_max_update": last, "mode": "wavefront" if wave else "colour"}
+
+
+def _solve_peer(engine, dist, world: int, max_iterations: int, tol: float, check_every: int):
+    """Fused path: a block of check_every sweeps is nothing but back-to-back pass kernels (the ghost rows travel
+    inside them); the only collective is the all-reduce of the per-sweep maxima at the end of the block."""
+    check_every = max(1, min(check_every, 4096))
+    done, conv, last = 0, 0, 0.0
+    while done < max_iterations and not conv:
+        k = min(check_every, max_iterations - done)
+        engine.clear_max(k)
+        engine.peer_run(k, 0)
+        m = engine.max_tensor(k).clone()
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        conv, last = _decide(m.cpu().numpy(), tol, done)
+        done += k
+    if engine.peer_timed_out():
+        raise RuntimeError("slab solve: a pass gave up waiting for a neighbouring rank's ghost rows")
+    return {"sweeps": done, "converged_at": conv, "last_max_update": last, "mode": "peer"}
+
+
+def solve_local_peer(engines, max_iterations: int, tol: float, check_every: int = 64):
+    """G slabs in THIS process on one GPU driving the fused-exchange kernels (attached with peer_connect_local):
+    passes are issued slab by slab so that every wait finds its flag already raised or raised by an earlier launch."""
+    import torch
+    TS = engines[0].TS
+    if not getattr(engines[0], "_local_connected", False):
+        for g in range(len(engines) - 1):
+            engines[g].peer_connect_local(1, engines[g + 1])
+            engines[g + 1].peer_connect_local(0, engines[g])
+        engines[0]._local_connected = True
+    check_every = max(1, min(check_every, 4096))
+    done, conv, last = 0, 0, 0.0
+    while done < max_iterations and not conv:
+        k = min(check_every, max_iterations - done)
+        for e in engines:
+            e.clear_max(k)
+        for j in range(0, k, TS):
+            for e in engines:
+                e.peer_run(min(TS, k - j), j)
+        m = engines[0].max_tensor(k).clone()
+        for e in engines[1:]:
+            m = torch.maximum(m, e.max_tensor(k))
+        conv, last = _decide(m.cpu().numpy(), tol, done)
+        done += k
+    if any(e.peer_timed_out() for e in engines):
+        raise RuntimeError("slab solve: a pass gave up waiting for a neighbouring slab's ghost rows")
+    return {"sweeps": done, "converged_at": conv, "last_max_update": last, "mode": "peer"}
 
 
 def solve_local(engines, max_iterations: int, tol: float, check_every: int = 64, mode: str = "auto"):

@@ -74,15 +74,50 @@ def test_slab_stopping_rule_matches_single_gpu(pcd, port):
     assert np.array_equal(got, want)
 
 
-def test_two_gpu_nccl_run(pcd, tmp_path):
+@pytest.mark.parametrize("shape,G,sweeps", [((203, 150), 2, 41), ((203, 150), 5, 41), ((640, 1100), 2, 37), ((900, 520), 3, 24)])
+def test_fused_exchange_on_one_gpu_bit_identical(pcd, port, shape, G, sweeps):
+    """The pass kernels that push ghost rows into the neighbouring slab and wait on its flag (pcd_slab_peer_*), with
+    all G slabs on one device: same field, same per-sweep maxima as the single-GPU solve."""
+    from poisson_caustic_design_b200 import slab
+    rng = np.random.RandomState(G + sweeps)
+    H, W = shape
+    D = rng.standard_normal((H, W))
+    D -= D.mean()
+    phi0 = rng.standard_normal((H, W))
+    engines = []
+    for g in range(G):
+        row0, rows = slab.partition(H, G, g)
+        e = slab.CudaSlabEngine(W, H, row0, rows, 0)
+        e.upload(slab.with_ghosts(D, row0, rows, e.GH), slab.with_ghosts(phi0, row0, rows, e.GH))
+        engines.append(e)
+    info = slab.solve_local_peer(engines, sweeps, 0.0, 16)
+    got = np.concatenate([e.download() for e in engines], axis=0)
+    # a second solve on the same slabs (sequence numbers keep counting)
+    for g, e in enumerate(engines):
+        row0, rows = slab.partition(H, G, g)
+        e.upload(None, slab.with_ghosts(phi0, row0, rows, e.GH))
+    info2 = slab.solve_local_peer(engines, 5, 0.0, 16)
+    got2 = np.concatenate([e.download() for e in engines], axis=0)
+    for e in engines:
+        e.close()
+    want, winfo = single_gpu(pcd, D, phi0, sweeps)
+    assert info["sweeps"] == sweeps and info["mode"] == "peer"
+    assert np.array_equal(got, want)
+    assert info["last_max_update"] == winfo["last_max_update"]
+    assert np.array_equal(got2, single_gpu(pcd, D, phi0, 5)[0]) and info2["sweeps"] == 5
+
+
+@pytest.mark.parametrize("mode", ["peer", "wavefront", "colour"])
+def test_two_gpu_nccl_run(pcd, tmp_path, mode):
     if pcd.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     script = os.path.join(ROOT, "tools", "slab_run.py")
     out = tmp_path / "out.npz"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", script, "--W", "512", "--H", "384", "--sweeps", "60", "--out", str(out)]
+           "--master-port", "29533", script, "--W", "1100", "--H", "640", "--sweeps", "61", "--out", str(out), "--mode", mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert f'"mode": "{mode}"' in r.stdout
     z = np.load(out)
-    want, _ = single_gpu(pcd, z["D"], z["phi0"], 60)
+    want, _ = single_gpu(pcd, z["D"], z["phi0"], 61)
     assert np.array_equal(z["phi"], want)

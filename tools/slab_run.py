@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--tol", type=float, default=0.0)
     ap.add_argument("--check_every", type=int, default=64)
     ap.add_argument("--out", default="")
-    ap.add_argument("--mode", default="auto", choices=["auto", "wavefront", "colour"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "peer", "wavefront", "colour"])
     a = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
