@@ -414,7 +414,7 @@ def run_slab(args, rank: int, local_rank: int, world: int):
                 "warmup": args.warmup, "ms_per_step": t * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "synthetic 8192x8192 Poisson problem, row slabs (BASELINE.json configs[4])",
-                           "domain": [W, H], "parallelism": f"row slabs x{world}, " + {"peer": "ghost rows stored into the neighbour's HBM by the pass kernel itself (NVLink peer memory, device-side flags)", "wavefront": "ghost rows exchanged with NCCL send/recv once per pass", "colour": "one ghost row exchanged with NCCL per colour phase"}[info["mode"]],
+                           "domain": [W, H], "parallelism": f"row slabs x{world}, " + {"peer": "ghost rows stored into the neighbour's HBM by the pass kernel itself (NVLink peer memory, device-side flags)", "wavefront": "single slab, no exchange" if world == 1 else "ghost rows exchanged with NCCL send/recv once per pass", "colour": "one ghost row exchanged with NCCL per colour phase"}[info["mode"]],
                            "sweeps_per_step": sweeps_per_step, "l2": "working set 1.6 GB >> L2"},
                 "roofline": {"bound": "hbm", "achieved": achieved / world, "peak": peak, "unit": "GB/s", "frac": achieved / world / peak,
                              "traffic": None, "kernel": "sor_wave_kernel", "peak_source": peak_src,
