@@ -143,19 +143,20 @@ struct InteriorRows {  // rows J .. NR-2 (compile-time recursion keeps every reg
     }
 };
 
-// One colour phase of one slab: interior rows first (they need nothing from other CTAs), then the halo
-// messages of the previous phase are consumed and the two boundary rows are updated and exported -- so a
-// message is in flight while both CTAs work on their interiors.  Within each group all shared-memory reads come
-// first, then the arithmetic, then the writes.
+// One colour phase of one slab: interior rows first (they need nothing from other CTAs), then the halo messages of
+// the neighbours' previous phase are consumed and the two boundary rows are updated and exported -- so a message is
+// in flight while both CTAs work on their interiors.  Within each group all shared-memory reads come first, then the
+// arithmetic, then the writes.  (Measured alternatives, all bit-exact and none faster -- tools/experiments/README.md:
+// boundary rows first with the polls for the next phase issued mid-interior; polls delayed by 1..5 interior rows;
+// re-polling both messages with both loads in flight.)
 template <int NR, int P0, bool FAST, bool EDGE>
-__device__ __forceinline__ void res_phase(Strip<NR> &s, double *__restrict__ smk, const int /*Kp*/, double &hu, double &hd,
-                                          const ResParams &p, double &lmax, const int k, uint4 *ll_up, uint4 *ll_dn,
-                                          const unsigned seq, const uint4 *in_t, const uint4 *in_b, const bool first) {
+__device__ __forceinline__ void res_phase(Strip<NR> &s, double *__restrict__ smk, double &hu, double &hd, const ResParams &p,
+                                          double &lmax, const int k, uint4 *ll_up, uint4 *ll_dn, const unsigned seq,
+                                          const uint4 *in_t, const uint4 *in_b, const bool first) {
     uint4 rt = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
-    if (!first) {  // polls for the cells the neighbours produced in their previous phase (seq-1)
-        if (in_t) rt = ll_issue(in_t);
-        if (in_b) rb = ll_issue(in_b);
-    }
+    const uint4 *pt = first ? nullptr : in_t, *pb = first ? nullptr : in_b;
+    if (pt) rt = ll_issue(pt);  // polls for the cells the neighbours produced in their previous phase (seq-1)
+    if (pb) rb = ll_issue(pb);
     double nb[NR];
     bool ok[NR];
     nb[0] = res_nb<NR, P0, 0>(smk);
@@ -163,10 +164,8 @@ __device__ __forceinline__ void res_phase(Strip<NR> &s, double *__restrict__ smk
     InteriorRows<NR, P0, FAST, EDGE, 1>::load(smk, nb);
     InteriorRows<NR, P0, FAST, EDGE, 1>::compute(s, nb, ok, p, lmax);
     InteriorRows<NR, P0, FAST, EDGE, 1>::store(s, smk, ok);
-    if (!first) {
-        if (in_t) hu = ll_consume(rt, in_t, seq - 1u);
-        if (in_b) hd = ll_consume(rb, in_b, seq - 1u);
-    }
+    if (pt) hu = ll_consume(rt, pt, seq - 1u);
+    if (pb) hd = ll_consume(rb, pb, seq - 1u);
     constexpr int q0 = P0 & 1, qb = (P0 + NR - 1) & 1;
     const bool ok0 = res_cell<NR, P0, FAST, EDGE, 0>(s, nb[0], hu, hd, p, lmax);
     bool okb = false;
@@ -265,6 +264,7 @@ __device__ __forceinline__ void res_body(const ResParams &p) {
         unsigned long long pend = 0ull;
         const int e = sweep - p.lag;
         if (tid == 0 && e >= 0) pend = *((const volatile unsigned long long *)(p.g_slot + e));  // consumed at the end of the sweep
+        int not_below = 0;
 #pragma unroll
         for (int colour = 0; colour < 2; ++colour) {
             const unsigned seq = 2u * (unsigned)sweep + (unsigned)colour + 1u;
@@ -276,16 +276,16 @@ __device__ __forceinline__ void res_body(const ResParams &p) {
                 const uint4 *ib = (has_dn && xb < W) ? in_bot + xb : nullptr;
                 const bool first = seq == 1u;
                 if (p0 == 0) {
-                    if (fast) res_phase<NR, 0, true, EDGE>(s, smk, Kp, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
-                    else res_phase<NR, 0, false, EDGE>(s, smk, Kp, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
+                    if (fast) res_phase<NR, 0, true, EDGE>(s, smk, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
+                    else res_phase<NR, 0, false, EDGE>(s, smk, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
                 } else {
-                    if (fast) res_phase<NR, 1, true, EDGE>(s, smk, Kp, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
-                    else res_phase<NR, 1, false, EDGE>(s, smk, Kp, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
+                    if (fast) res_phase<NR, 1, true, EDGE>(s, smk, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
+                    else res_phase<NR, 1, false, EDGE>(s, smk, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
                 }
             }
-            if (colour == 1) {
-                lmax = warp_max(lmax);
-                if ((tid & 31) == 0 && lmax > 0.0) atomicMax(&blkmax[sweep & 1], (unsigned long long)__double_as_longlong(lmax));
+            if (colour == 0) {
+                __syncthreads();
+            } else {
                 if (tid == 0 && e >= 0 && conv_at == 0) {
                     while ((unsigned)pend != (unsigned)p.P) pend = *((const volatile unsigned long long *)(p.g_slot + e));
                     if ((pend >> 32) == 0ull) {
@@ -293,16 +293,26 @@ __device__ __forceinline__ void res_body(const ResParams &p) {
                         s_stop = sweep + 1;
                     }
                 }
+                // the barrier that ends the sweep also carries the CTA's verdict: is any |delta| of this sweep >= tol ?
+                not_below = __syncthreads_or(lmax >= p.tol);
             }
+        }
+        // The per-sweep maximum itself is only ever read for sweeps at which every CTA is below tol (the sweep the solve
+        // stops at) and for the last sweeps of a launch that hits its cap (the host scans those): reduce it only then.
+        const bool need_max = !not_below || sweep + p.lag + 3 >= max_it;
+        if (need_max) {
+            const double wm = warp_max(lmax);
+            if ((tid & 31) == 0 && wm > 0.0) atomicMax(&blkmax[0], (unsigned long long)__double_as_longlong(wm));
             __syncthreads();
         }
-        // publish this sweep: arrival + verdict in one atomic, max separately (host reads it afterwards)
+        // publish this sweep: arrival + verdict in one atomic
         if (tid == 0) {
-            const unsigned long long bm = blkmax[sweep & 1];
-            blkmax[sweep & 1] = 0ull;
-            const bool below = __longlong_as_double((long long)bm) < p.tol;
-            atomicAdd(p.g_slot + sweep, 1ull | (below ? 0ull : (1ull << 32)));
-            if (bm) atomicMax(p.g_max + sweep, bm);
+            atomicAdd(p.g_slot + sweep, 1ull | (not_below ? (1ull << 32) : 0ull));
+            if (need_max) {
+                const unsigned long long bm = blkmax[0];
+                blkmax[0] = 0ull;
+                if (bm) atomicMax(p.g_max + sweep, bm);
+            }
         }
         if (s_stop == sweep + 1 || sweep + 1 >= max_it) break;
     }

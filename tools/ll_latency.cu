@@ -69,6 +69,57 @@ __global__ void chain(uint4 *ll, int W, int phases, int active, int backoff, lon
     if (t == 0 && cta == P / 2) *cycles = clock64() - t0;
 }
 
+
+// chain2: the solver's phase structure with emulated compute.  Per phase: polls for the neighbours' previous
+// messages are issued at the start and then every `gap` cycles (DEPTH polls in flight per slot), the thread
+// "computes" for I cycles, consumes the messages (re-polling one at a time if none of the early polls saw them),
+// "computes" B cycles, sends its own messages, __syncthreads.
+__device__ __forceinline__ void spin_until(long long t) { while (clock64() < t) { } }
+template <int DEPTH>
+__global__ void chain2(uint4 *ll, int W, int phases, int I, int B, int gap, long long *cycles, unsigned *sink) {
+    const int cta = blockIdx.x, P = gridDim.x, t = threadIdx.x;
+    uint4 *up = cta > 0 ? ll + ((size_t)(cta - 1) * 2 + 1) * W : nullptr;
+    uint4 *dn = cta + 1 < P ? ll + ((size_t)(cta + 1) * 2) * W : nullptr;
+    const uint4 *it = ll + ((size_t)cta * 2) * W + t, *ib = ll + ((size_t)cta * 2 + 1) * W + t;
+    const bool hu = cta > 0, hd = cta + 1 < P;
+    unsigned acc = 0;
+    long long t0 = clock64();
+    for (int ph = 1; ph <= phases; ++ph) {
+        const long long s0 = clock64();
+        const unsigned want = (unsigned)(ph - 1);
+        uint4 rt[DEPTH], rb[DEPTH];
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+            if (d) spin_until(s0 + (long long)d * gap);
+            if (hu) rt[d] = ll_load(it);
+            if (hd) rb[d] = ll_load(ib);
+        }
+        spin_until(s0 + I);
+        if (hu) {
+            bool got = false;
+            uint4 r;
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) if (!got && rt[d].y >= want && rt[d].w >= want) { got = true; r = rt[d]; }
+            if (!got) { r = ll_load(it); while (r.y < want || r.w < want) r = ll_load(it); }
+            acc += r.x;
+        }
+        if (hd) {
+            bool got = false;
+            uint4 r;
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) if (!got && rb[d].y >= want && rb[d].w >= want) { got = true; r = rb[d]; }
+            if (!got) { r = ll_load(ib); while (r.y < want || r.w < want) r = ll_load(ib); }
+            acc += r.x;
+        }
+        spin_until(clock64() + B);
+        if (up) ll_store(up + t, ph + acc * 0, t, ph);
+        if (dn) ll_store(dn + t, ph, t, ph);
+        __syncthreads();
+    }
+    if (t == 0 && cta == P / 2) *cycles = clock64() - t0;
+    if (acc == 0xdeadbeef) *sink = acc;
+}
+
 // plain L2 load latency (pointer chase, one thread)
 __global__ void chase(const unsigned *next, int iters, long long *cycles, unsigned *sink) {
     unsigned i = 0;
@@ -116,5 +167,21 @@ int main() {
             CK(cudaDeviceSynchronize());
             printf("chain: 148 CTAs x %3d polling threads, backoff %3d ns: %.0f cycles per phase\n", a, b, (double)*cyc / phases);
         }
+    {   // solver-shaped phases with emulated compute
+        unsigned *sink; CK(cudaMalloc(&sink, 4));
+        struct Cfg { int depth, I, B, gap; };
+        Cfg cfgs[] = {{1, 0, 0, 0}, {1, 700, 300, 0}, {2, 700, 300, 350}, {3, 700, 300, 230}, {4, 700, 300, 175}, {1, 1000, 300, 0}, {3, 1000, 300, 330},
+                      {4, 1000, 300, 250}, {1, 400, 200, 0}, {3, 400, 200, 130}, {4, 1400, 300, 350}};
+        for (Cfg c : cfgs) {
+            CK(cudaMemset(ll, 0, (size_t)148 * 2 * W * 16));
+            int phases = 4000;
+            void *args[] = {&ll, (void *)&W, &phases, &c.I, &c.B, &c.gap, &cyc, &sink};
+            void *fn = c.depth == 1 ? (void *)chain2<1> : c.depth == 2 ? (void *)chain2<2> : c.depth == 3 ? (void *)chain2<3> : (void *)chain2<4>;
+            CK(cudaLaunchCooperativeKernel(fn, dim3(148), dim3(512), args, 0, 0));
+            CK(cudaDeviceSynchronize());
+            printf("chain2: depth %d interior %4d boundary %3d gap %3d: %.0f cycles per phase (compute alone %d)\n", c.depth, c.I, c.B, c.gap,
+                   (double)*cyc / phases, c.I + c.B);
+        }
+    }
     return 0;
 }
