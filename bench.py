@@ -68,6 +68,15 @@ def load_traffic():
         return None
 
 
+def wave_traffic(traffic, cells):
+    """DRAM bytes of one wavefront pass over `cells` cells, scaled from the committed 8192^2 capture; None when the
+    working set (3 arrays) is not far beyond the 126 MB L2, where the capture does not transfer."""
+    w = (traffic or {}).get("sor_wave_kernel")
+    if not w or 24.0 * cells < 4 * 126e6:
+        return None
+    return int(w["dram_bytes_per_cell_per_launch"] * cells)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -319,7 +328,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     achieved = alg_bytes / (totals["kernel_ms"] * 1e-3) / 1e9 if totals["kernel_ms"] > 0 else 0.0
     traffic = load_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic["dram_bytes_per_launch"] if (traffic and totals["path"] == "resident") else None,
+                "traffic": (traffic["dram_bytes_per_launch"] if totals["path"] == "resident" else wave_traffic(traffic, W * H)) if traffic else None,
                 "kernel": {"resident": "sor_resident_kernel", "tiled": "sor_wave_kernel"}.get(totals["path"], "sor_colour_kernel"),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / max(totals["launches"], 1),
@@ -417,7 +426,7 @@ def run_slab(args, rank: int, local_rank: int, world: int):
                            "domain": [W, H], "parallelism": f"row slabs x{world}, " + {"peer": "ghost rows stored into the neighbour's HBM by the pass kernel itself (NVLink peer memory, device-side flags)", "wavefront": "single slab, no exchange" if world == 1 else "ghost rows exchanged with NCCL send/recv once per pass", "colour": "one ghost row exchanged with NCCL per colour phase"}[info["mode"]],
                            "sweeps_per_step": sweeps_per_step, "l2": "working set 1.6 GB >> L2"},
                 "roofline": {"bound": "hbm", "achieved": achieved / world, "peak": peak, "unit": "GB/s", "frac": achieved / world / peak,
-                             "traffic": None, "kernel": "sor_wave_kernel", "peak_source": peak_src,
+                             "traffic": wave_traffic(load_traffic(), W * H // world), "kernel": "sor_wave_kernel", "peak_source": peak_src,
                              "note": "per-GPU algorithmic GB/s (24 B/cell/sweep); whole job = achieved x n_gpus"},
                 "poisson_gbs": achieved, "gpu_launches": int(launches * world), "clocks": clocks,
                 "e2e": {"value": sweeps / t, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * sweeps_per_step,
