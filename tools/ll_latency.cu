@@ -120,6 +120,62 @@ __global__ void chain2(uint4 *ll, int W, int phases, int I, int B, int gap, long
     if (acc == 0xdeadbeef) *sink = acc;
 }
 
+
+// chain3: like chain2 but the halo is received by NPOLL dedicated warps that poll continuously (MSG loads in flight
+// per lane) and hand the values to the compute warps through shared memory at the phase barrier.  Compute warps:
+// "boundary" B cycles, send, "interior" I cycles.  blockDim = 512 + 32*NPOLL.
+template <int NPOLL>
+__global__ void __launch_bounds__(512 + 32 * NPOLL, 1) chain3(uint4 *ll, int W, int phases, int I, int B, long long *cycles, unsigned *sink) {
+    __shared__ unsigned halo[2][1024];
+    const int cta = blockIdx.x, P = gridDim.x, t = threadIdx.x;
+    uint4 *up = cta > 0 ? ll + ((size_t)(cta - 1) * 2 + 1) * W : nullptr;
+    uint4 *dn = cta + 1 < P ? ll + ((size_t)(cta + 1) * 2) * W : nullptr;
+    const bool hu = cta > 0, hd = cta + 1 < P;
+    unsigned acc = 0;
+    long long t0 = clock64();
+    if (t < 512) {
+        for (int ph = 1; ph <= phases; ++ph) {
+            if (ph > 1) acc += halo[0][t] + halo[1][t];     // halo of the previous phase, delivered by the poll warps
+            spin_until(clock64() + B);
+            if (up) ll_store(up + t, ph + acc * 0, t, ph);
+            if (dn) ll_store(dn + t, ph, t, ph);
+            spin_until(clock64() + I);
+            __syncthreads();
+        }
+    } else {
+        constexpr int MSG = 1024 / (32 * NPOLL);            // messages per lane (512 from above + 512 from below)
+        const int lane = t - 512;
+        for (int ph = 1; ph <= phases; ++ph) {
+            // messages of THIS phase (the compute warps of the neighbours send them B cycles into the phase)
+            const uint4 *base = ll + (size_t)cta * 2 * W;   // message id (0..1023) lives at base[(id >> 9) * W + (id & 511)]
+            unsigned need = 0;
+            uint4 r[MSG];
+#pragma unroll
+            for (int m = 0; m < MSG; ++m) {
+                const int id = lane + m * 32 * NPOLL;
+                if (id < 512 ? hu : hd) need |= 1u << m;
+            }
+            while (need) {
+#pragma unroll
+                for (int m = 0; m < MSG; ++m) {
+                    const int id = lane + m * 32 * NPOLL;
+                    if (need >> m & 1) r[m] = ll_load(base + (size_t)(id >> 9) * W + (id & 511));
+                }
+#pragma unroll
+                for (int m = 0; m < MSG; ++m)
+                    if ((need >> m & 1) && r[m].y >= (unsigned)ph && r[m].w >= (unsigned)ph) {
+                        const int id = lane + m * 32 * NPOLL;
+                        halo[id >> 9][id & 511] = r[m].x;
+                        need &= ~(1u << m);
+                    }
+            }
+            __syncthreads();
+        }
+    }
+    if (t == 0 && cta == P / 2) *cycles = clock64() - t0;
+    if (acc == 0xdeadbeef) *sink = acc;
+}
+
 // plain L2 load latency (pointer chase, one thread)
 __global__ void chase(const unsigned *next, int iters, long long *cycles, unsigned *sink) {
     unsigned i = 0;
@@ -180,6 +236,21 @@ int main() {
             CK(cudaLaunchCooperativeKernel(fn, dim3(148), dim3(512), args, 0, 0));
             CK(cudaDeviceSynchronize());
             printf("chain2: depth %d interior %4d boundary %3d gap %3d: %.0f cycles per phase (compute alone %d)\n", c.depth, c.I, c.B, c.gap,
+                   (double)*cyc / phases, c.I + c.B);
+        }
+    }
+    {   // dedicated polling warps
+        unsigned *sink; CK(cudaMalloc(&sink, 4));
+        struct Cfg { int npoll, I, B; };
+        Cfg cfgs[] = {{2, 0, 0}, {2, 700, 300}, {2, 1070, 300}, {1, 1070, 300}, {4, 1070, 300}, {2, 1400, 300}, {2, 400, 200}};
+        for (Cfg c : cfgs) {
+            CK(cudaMemset(ll, 0, (size_t)148 * 2 * W * 16));
+            int phases = 4000;
+            void *args[] = {&ll, (void *)&W, &phases, &c.I, &c.B, &cyc, &sink};
+            void *fn = c.npoll == 1 ? (void *)chain3<1> : c.npoll == 2 ? (void *)chain3<2> : (void *)chain3<4>;
+            CK(cudaLaunchCooperativeKernel(fn, dim3(148), dim3(512 + 32 * c.npoll), args, 0, 0));
+            CK(cudaDeviceSynchronize());
+            printf("chain3: %d poll warps, boundary %3d interior %4d: %.0f cycles per phase (compute alone %d)\n", c.npoll, c.B, c.I,
                    (double)*cyc / phases, c.I + c.B);
         }
     }
