@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- transport iterations/s and Poisson-sweep GB/s at a 1024x1024 grid (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c4|c2|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload c4|c1|c2k|c4k|c5|c5slab] [--distribute]
 
 One "step" = one optimal-transport iteration (dual-cell areas -> density mismatch -> rasterise -> mean
 removal -> Poisson solve (~10^4 red-black SOR sweeps, tol 1e-7, warm-started) -> gradient step on the
 mesh vertices) on the synthetic 1024x1024 high-contrast density of BASELINE.json configs[3] (mesh
 256x256).  N>1: one process per GPU (torchrun), every rank designs its own lens (independent units,
-no data-path collective) -> weak scaling.
+no data-path collective) -> weak scaling.  Large grids: `--workload c5 --distribute` runs ONE
+8192x8192 design whose Poisson solves are spread over the N GPUs as row slabs (ghost rows stored into the
+neighbour's HBM by the pass kernel itself) -> strong scaling; `--workload c5slab` times the slab solver alone.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   roofline      dominant kernel (the resident SOR kernel): algorithmic bytes = 24 B x W x H x sweeps
@@ -42,11 +45,12 @@ WORKLOADS = {
     "c4": (256, 1024, 1024, 1024, "synthetic 1024x1024 high-contrast density, mesh 256x256 (BASELINE.json configs[3])"),
     "c1": (100, 400, 400, 400, "synthetic 400x400 density, mesh 100x100 (size of BASELINE.json configs[0])"),
     "c2k": (512, 2048, 2048, 2048, "synthetic 2048x2048 density, mesh 512x512 (wavefront K-SOR path)"),
-    "c5": (2048, 8192, 8192, 8192, "synthetic 8192x8192 density, mesh 2048x2048 (BASELINE.json configs[4], one GPU)"),
+    "c4k": (1024, 4096, 4096, 4096, "synthetic 4096x4096 density, mesh 1024x1024 (wavefront K-SOR path)"),
+    "c5": (2048, 8192, 8192, 8192, "synthetic 8192x8192 density, mesh 2048x2048 (BASELINE.json configs[4])"),
 }
 # sweeps of the first transport solve (measured with the CUDA path; the reference's lexicographic
 # ordering needs 3-10 % more) -- used only to extrapolate the CPU sample to a full iteration
-EXPECTED_SWEEPS = {"c4": 11000, "c1": 4300, "c2k": 21500, "c5": 85000}
+EXPECTED_SWEEPS = {"c4": 11000, "c1": 4300, "c2k": 21500, "c4k": 48000, "c5": 85000}
 BYTES_PER_CELL_SWEEP = 24.0
 
 
@@ -253,10 +257,18 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    setup, img, desc = make_workload(args.workload, rank)
+    # --distribute: ONE design for the whole job; its Poisson solves are spread over the ranks as row slabs (strong
+    # scaling), every other stage is replicated.  Default: one design per GPU (replicas, weak scaling).
+    distributed = bool(args.distribute)
+    setup, img, desc = make_workload(args.workload, 0 if distributed else rank)
     W, H, V = setup.res_x, setup.res_y, setup.mesh_nx * setup.mesh_ny
     cd = P.from_setup(setup, device=local_rank)
     cd.initialize_solvers(img)
+    hook = None
+    if distributed:
+        from poisson_caustic_design_b200 import slab
+        hook = slab.SlabSolveHook(cd, dist, rank, world, local_rank)
+    designs = 1 if distributed else world
     for _ in range(args.warmup):
         cd.perform_transport_iteration()
 
@@ -286,7 +298,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_max = float(t.item())
-    value = world * args.steps / (t_max * 1e-3)
+    value = designs * args.steps / (t_max * 1e-3)
+    if hook is not None and hook.error is not None:
+        raise hook.error
 
     # ---- end to end through host buffers --------------------------------------------------------
     pin = lambda n: torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()  # noqa: E731
@@ -313,9 +327,12 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         t = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_wall = float(t.item())
-    e2e = {"value": world * args.steps / e_wall, "unit": UNIT, "h2d_bytes_per_step": 2 * V * 8,
+    e2e = {"value": designs * args.steps / e_wall, "unit": UNIT, "h2d_bytes_per_step": 2 * V * 8,
            "d2h_bytes_per_step": 5 * V * 8 + 8}
 
+    mode_used = hook.solves[-1]["mode"] if hook is not None and hook.solves else None
+    if hook is not None:
+        hook.close()
     if rank != 0:
         cd.close()
         if dist is not None:
@@ -326,9 +343,11 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     sweeps = totals["sweeps"]
     alg_bytes = BYTES_PER_CELL_SWEEP * W * H * sweeps
     achieved = alg_bytes / (totals["kernel_ms"] * 1e-3) / 1e9 if totals["kernel_ms"] > 0 else 0.0
+    if distributed:
+        achieved /= world   # per GPU: every rank moves 1/world of the cells
     traffic = load_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (traffic["dram_bytes_per_launch"] if totals["path"] == "resident" else wave_traffic(traffic, W * H)) if traffic else None,
+                "traffic": (traffic["dram_bytes_per_launch"] if totals["path"] == "resident" else wave_traffic(traffic, W * H // (world if distributed else 1))) if traffic else None,
                 "kernel": {"resident": "sor_resident_kernel", "tiled": "sor_wave_kernel"}.get(totals["path"], "sor_colour_kernel"),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / max(totals["launches"], 1),
@@ -340,12 +359,14 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                          "temporal blocking: each launch applies 2 sweeps per HBM pass (12 B/cell/sweep of real traffic)")}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": t_max / args.steps, "higher_is_better": True, "scaling": "strong" if distributed else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "mesh": [setup.mesh_nx, setup.mesh_ny], "domain": [W, H],
-                   "parallelism": "1 GPU" if world == 1 else f"replicas x{world} (one lens design per GPU, no collective)",
+                   "parallelism": ("1 GPU" if world == 1 else
+                                   f"ONE design, Poisson solves on row slabs x{world} ({mode_used} exchange), other stages replicated"
+                                   if distributed else f"replicas x{world} (one lens design per GPU, no collective)"),
                    "l2": "flushed between steps (256 MiB memset, untimed)", "solver_path": totals["path"]},
-        "poisson_sweeps_per_sec": world * sweeps / (totals["kernel_ms"] * 1e-3) if totals["kernel_ms"] > 0 else None,
+        "poisson_sweeps_per_sec": designs * sweeps / (totals["kernel_ms"] * 1e-3) if totals["kernel_ms"] > 0 else None,
         "poisson_sweeps_per_step": sweeps / args.steps,
         "poisson_gbs": achieved,
         "roofline": roofline,
@@ -445,6 +466,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["c5slab"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--distribute", action="store_true",
+                    help="one design for the whole job: Poisson solves spread over the GPUs as row slabs (strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))

@@ -122,6 +122,15 @@ int pcd_event_elapsed_ms(pcd_ctx *ctx, int slot_start, int slot_stop, double *ms
 /* evicts L2 by writing a 256 MiB scratch buffer on the context's stream (bench hygiene between steps) */
 int pcd_flush_l2(pcd_ctx *ctx);
 /* stage entry points (per-stage parity tests drive these with the oracle's inputs) */
+/* Poisson solves of a context can be handed to an external solver (the multi-GPU slab driver, slab.py): the hook
+ * receives DEVICE pointers of the context's width x height arrays (D read-only, phi in/out; the reference call it
+ * replaces is poisson_solver, src/solver.h:8, as issued at src/caustic_design.cpp:222,311).  It runs on the calling
+ * thread after the context's stream has been drained and must leave phi complete on the device when it returns;
+ * a non-zero return value becomes the status of the pcd_* call that needed the solve.  NULL restores the built-in
+ * solver. */
+typedef int (*pcd_solve_hook)(void *user, const double *D_dev, double *phi_dev, int width, int height, int max_iterations,
+                              double tol, pcd_solve_info *info);
+int pcd_set_solve_hook(pcd_ctx *ctx, pcd_solve_hook hook, void *user);
 int pcd_stage_errors(pcd_ctx *ctx);                                       /* caustic_design.cpp:194-209 */
 int pcd_stage_raster(pcd_ctx *ctx);                                       /* :212-213, no mean removal */
 int pcd_stage_subtract_average(pcd_ctx *ctx);                             /* :221 */
@@ -172,6 +181,10 @@ int pcd_slab_pass(pcd_slab *s, int nsweeps, int slot);
 int pcd_slab_pass_part(pcd_slab *s, int nsweeps, int slot, int row_begin, int row_count, void *cuda_stream);
 int pcd_slab_flip(pcd_slab *s);
 int pcd_slab_clear_max(pcd_slab *s, int n_slots);
+/* D and phi of the slab (ghost rows included) from / owned rows of phi back to full width x height DEVICE arrays
+ * on the slab's device (device-to-device, on the slab's stream; load waits for it) */
+int pcd_slab_load_device(pcd_slab *s, const double *D_full_dev, const double *phi_full_dev);
+int pcd_slab_store_device(pcd_slab *s, double *phi_full_dev);
 /* Ghost-row exchange FUSED into the pass (no host-side collective on the data path): the kernel stores the
  * pcd_slab_ghost_rows() rows next to a slab edge straight into the neighbour's field (peer memory over NVLink)
  * and raises a sequence flag there; the neighbour's next pass waits for that flag on the device.  Neighbours are

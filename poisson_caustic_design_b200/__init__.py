@@ -105,6 +105,9 @@ ABI = [
     ("pcd_slab_current", C.c_int, [C.c_void_p]),
     ("pcd_slab_has_nan", C.c_int, [C.c_void_p]),
     ("pcd_slab_clear_max", C.c_int, [C.c_void_p, C.c_int]),
+    ("pcd_slab_load_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("pcd_slab_store_device", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("pcd_set_solve_hook", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pcd_slab_peer_handle_bytes", C.c_int, []),
     ("pcd_slab_peer_export", C.c_int, [C.c_void_p, C.c_void_p]),
     ("pcd_slab_peer_connect_ipc", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),

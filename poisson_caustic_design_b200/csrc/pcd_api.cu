@@ -180,6 +180,13 @@ int pcd_initialize_solvers(pcd_ctx *ctx, const double *image) {
     return PCD_OK;
 }
 
+int pcd_set_solve_hook(pcd_ctx *ctx, pcd_solve_hook hook, void *user) {
+    NEED_CTX(ctx);
+    ctx->solve_hook = hook;
+    ctx->solve_hook_user = hook ? user : nullptr;
+    return PCD_OK;
+}
+
 int pcd_stage_errors(pcd_ctx *ctx) { NEED_INIT(ctx); return k_errors(ctx); }
 int pcd_stage_raster(pcd_ctx *ctx) {
     NEED_INIT(ctx);

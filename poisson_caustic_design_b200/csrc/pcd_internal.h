@@ -117,12 +117,23 @@ struct pcd_ctx {
     pcd_solve_info totals{};
     cudaEvent_t events[8] = {};
     void *l2_scratch = nullptr;
+    pcd_solve_hook solve_hook = nullptr;  // external Poisson solver (pcd_set_solve_hook)
+    void *solve_hook_user = nullptr;
 };
 
 namespace pcd {
 // solve on the context's grid and fold the result into ctx->last / ctx->totals
 inline int ctx_solve(pcd_ctx *c, const double *D_dev, double *x_dev, double tol) {
-    int rc = solver_run(&c->solver, D_dev, x_dev, 100000, tol, &c->last);  // cap 100000: src/caustic_design.cpp:222,311
+    int rc;
+    if (c->solve_hook) {  // external (multi-GPU) solver: sees finished inputs, leaves a finished phi
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { set_error("stream synchronize before the solve hook: %s", cudaGetErrorString(e)); return PCD_ERR_CUDA; }
+        c->last = pcd_solve_info{};
+        rc = c->solve_hook(c->solve_hook_user, D_dev, x_dev, c->cfg.res_x, c->cfg.res_y, 100000, tol, &c->last);
+        if (rc != PCD_OK) set_error("the solve hook failed with status %d", rc);
+    } else {
+        rc = solver_run(&c->solver, D_dev, x_dev, 100000, tol, &c->last);  // cap 100000: src/caustic_design.cpp:222,311
+    }
     c->totals.sweeps += c->last.sweeps;
     c->totals.launches += c->last.launches;
     c->totals.kernel_ms += c->last.kernel_ms;

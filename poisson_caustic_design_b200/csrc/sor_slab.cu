@@ -181,6 +181,38 @@ int pcd_slab_upload(pcd_slab *s, const double *D_rows, const double *phi_rows) {
     return PCD_OK;
 }
 
+// the same from full W x H device arrays (multi-GPU solve hook: every rank holds the whole right-hand side)
+int pcd_slab_load_device(pcd_slab *s, const double *D_full, const double *phi_full) {
+    if (!s || !D_full || !phi_full) { set_error("null argument"); return PCD_ERR_INVALID; }
+    PCD_TRY(select_device(s->device));
+    const size_t W = (size_t)s->W;
+    const size_t all = (size_t)(s->rows + 2 * s->GH) * W * sizeof(double);
+    const int lo = s->row0 - s->GH > 0 ? s->row0 - s->GH : 0;
+    const int hi = s->row0 + s->rows + s->GH < s->H ? s->row0 + s->rows + s->GH : s->H;
+    const size_t off = (size_t)(lo - (s->row0 - s->GH)) * W, cnt = (size_t)(hi - lo) * W * sizeof(double);
+    PCD_CUDA(cudaMemsetAsync(s->D, 0, all, s->stream));       // ghost rows outside the grid
+    PCD_CUDA(cudaMemsetAsync(s->phi[0], 0, all, s->stream));
+    PCD_CUDA(cudaMemcpyAsync(s->D + off, D_full + (size_t)lo * W, cnt, cudaMemcpyDeviceToDevice, s->stream));
+    PCD_CUDA(cudaMemcpyAsync(s->phi[0] + off, phi_full + (size_t)lo * W, cnt, cudaMemcpyDeviceToDevice, s->stream));
+    s->cur = 0;
+    PCD_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
+    slab_mask_kernel<<<dim3((s->W + 255) / 256, s->rows), 256, 0, s->stream>>>(s->D, s->mask, s->W, s->H, s->row0, s->rows, s->GH,
+                                                                             s->d_flag);
+    PCD_LAUNCHED();
+    s->launches++;
+    PCD_CUDA(cudaMemcpyAsync(&s->has_nan, s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    PCD_CUDA(cudaStreamSynchronize(s->stream));
+    return PCD_OK;
+}
+
+int pcd_slab_store_device(pcd_slab *s, double *phi_full) {
+    if (!s || !phi_full) { set_error("null argument"); return PCD_ERR_INVALID; }
+    PCD_TRY(select_device(s->device));
+    PCD_CUDA(cudaMemcpyAsync(phi_full + (size_t)s->row0 * s->W, s->phi[s->cur] + (size_t)s->GH * s->W,
+                             (size_t)s->rows * s->W * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    return PCD_OK;
+}
+
 int pcd_slab_download(pcd_slab *s, double *phi_owned_rows) {
     if (!s || !phi_owned_rows) { set_error("null argument"); return PCD_ERR_INVALID; }
     PCD_TRY(select_device(s->device));

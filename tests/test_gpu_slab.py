@@ -121,3 +121,57 @@ def test_two_gpu_nccl_run(pcd, tmp_path, mode):
     z = np.load(out)
     want, _ = single_gpu(pcd, z["D"], z["phi0"], 61)
     assert np.array_equal(z["phi"], want)
+
+
+def _design(pcd, res_w, aspect, seed, device=0):
+    from poisson_caustic_design_b200 import synth
+    W = 4 * res_w
+    H = int(W / aspect)
+    image = synth.synth_density(W, H, seed)
+    cd = pcd.from_setup(synth.Setup(res_w, W, H), device)
+    cd.initialize_solvers(image)
+    return cd
+
+
+def test_solve_hook_on_one_gpu_matches_the_builtin_solver(pcd):
+    """The slab driver installed as the context's Poisson solver (pcd_set_solve_hook), world size 1: same sweep
+    schedule as the built-in large-grid solver, so steps and fields are bit-identical."""
+    from poisson_caustic_design_b200 import slab
+    ref = _design(pcd, 320, 4.0, 7)          # domain 1280 x 320: too wide for the resident kernel -> wavefront path
+    steps_ref = [ref.perform_transport_iteration() for _ in range(2)]
+    info_ref = ref.last_solve_info()
+    ref.perform_height_map_iteration(0)
+    got = _design(pcd, 320, 4.0, 7)
+    hook = slab.SlabSolveHook(got, None, 0, 1, 0)
+    steps = [got.perform_transport_iteration() for _ in range(2)]
+    info = got.last_solve_info()
+    got.perform_height_map_iteration(0)
+    assert hook.error is None and len(hook.solves) == 3
+    assert info_ref["path"] == "tiled" and info["path"] == "tiled"
+    assert info["sweeps"] == info_ref["sweeps"] and info["converged_at"] == info_ref["converged_at"]
+    assert steps == steps_ref
+    for name in ("phi", "h", "target_x", "target_y", "source_z"):
+        assert np.array_equal(got.get(name), ref.get(name)), name
+    hook.close()
+    # the hook is gone: the context solves on its own again
+    assert got.perform_transport_iteration() == ref.perform_transport_iteration()
+    got.close(); ref.close()
+
+
+def test_two_gpu_design_matches_one_gpu(pcd, tmp_path):
+    if pcd.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    script = os.path.join(ROOT, "tools", "dist_design_run.py")
+    out = tmp_path / "design.npz"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", script, "--res_w", "320", "--aspect", "4", "--iters", "2", "--out", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    z = np.load(out)
+    ref = _design(pcd, 320, 4.0, 7)
+    steps_ref = [ref.perform_transport_iteration() for _ in range(2)]
+    ref.perform_height_map_iteration(0)
+    assert list(z["steps"]) == steps_ref
+    for name, key in (("phi", "phi"), ("h", "h"), ("target_x", "tx"), ("target_y", "ty"), ("source_z", "sz")):
+        assert np.array_equal(z[key], ref.get(name)), name
+    ref.close()
