@@ -350,7 +350,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                 "traffic": (traffic["dram_bytes_per_launch"] if totals["path"] == "resident" else wave_traffic(traffic, W * H // (world if distributed else 1))) if traffic else None,
                 "kernel": {"resident": "sor_resident_kernel", "tiled": "sor_wave_kernel"}.get(totals["path"], "sor_colour_kernel"),
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes / max(totals["launches"], 1),
+                "algorithmic_bytes_per_launch": alg_bytes / max(totals["launches"], 1) / (world if distributed else 1),
                 "sweeps_per_launch": sweeps / max(totals["launches"], 1),
                 "kernel_ms_per_launch": totals["kernel_ms"] / max(totals["launches"], 1),
                 "kernel_share_of_step": totals["kernel_ms"] / dev_ms if dev_ms > 0 else None,
