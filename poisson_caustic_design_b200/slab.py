@@ -1,18 +1,23 @@
 """Row-slab Poisson solve across GPUs: one process per GPU, torch.distributed for the plumbing.
 
 The W x H grid is cut into `world` contiguous row slabs, each held with GH ghost rows above and below.
-Two ways to advance, both bit-identical to the single-GPU solve run for the same number of sweeps (updates of
+Three ways to advance, all bit-identical to the single-GPU solve run for the same number of sweeps (updates of
 one colour are order-independent, max is exact):
 
-* wavefront mode (default): ``engine.pass_`` runs up to TS full red-black sweeps over the slab in one kernel
-  (temporal blocking, csrc/sor_tiled.cu); afterwards every rank sends its GH boundary rows to each neighbour
-  (NCCL send/recv over NVLink; gloo in the CPU tests) -- ONE exchange per TS sweeps;
+* peer mode (default on GPUs when the neighbours' memory can be attached through CUDA IPC): the ghost-row exchange
+  is fused into the wavefront pass kernel -- plain stores into the neighbour's field over NVLink plus a sequence
+  flag the neighbour's next pass waits on (csrc/sor_tiled.cu, PEER variant); a block of sweeps is back-to-back
+  kernel launches issued from C, no host-side collective on the data path;
+* wavefront mode: ``engine.pass_`` runs up to TS full red-black sweeps over the slab in one kernel (temporal
+  blocking); afterwards every rank sends its GH boundary rows to each neighbour (NCCL send/recv over NVLink; gloo
+  in the CPU tests) -- ONE exchange per TS sweeps;
 * colour mode (D has NaN holes, or slabs thinner than GH rows): one kernel per colour phase, one ghost row
   exchanged per phase.
 
 Every ``check_every`` sweeps the per-sweep maxima are all-reduced (MAX) and every rank takes the same stop
 decision.  ``engine`` abstracts the local slab (CudaSlabEngine below; the CPU tests plug a numpy engine in to
-exercise this host logic without a GPU).
+exercise this host logic without a GPU).  ``SlabSolveHook`` installs the distributed solve as the Poisson solver
+of a whole caustic design (include/pcd.h: pcd_set_solve_hook).
 """
 from __future__ import annotations
 
