@@ -44,3 +44,25 @@ def test_product_does_not_touch_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 for needle in ("pcd_oracle.h", "libpcd_oracle", "libpcd_ref", "pcdo_", "import oracle", "from oracle"):
                     assert needle not in src, f"{f} references the oracle ({needle})"
+
+
+def test_argument_errors_need_no_device(pcd):
+    """Entry points reject bad handles / arguments with PCD_ERR_INVALID before touching CUDA (and say why)."""
+    L = pcd.lib()
+    null = ctypes.c_void_p()
+    buf = (ctypes.c_ubyte * 256)()
+    t = ctypes.c_int(0)
+    assert L.pcd_set_solve_hook(null, None, None) == pcd.PCD_ERR_INVALID
+    assert L.pcd_slab_peer_export(null, buf) == pcd.PCD_ERR_INVALID
+    assert L.pcd_slab_peer_connect_ipc(null, 0, buf, 0, 16) == pcd.PCD_ERR_INVALID
+    assert L.pcd_slab_peer_connect_local(null, 0, null) == pcd.PCD_ERR_INVALID
+    assert L.pcd_slab_peer_run(null, 2, 0) == pcd.PCD_ERR_INVALID
+    assert L.pcd_slab_peer_status(null, ctypes.byref(t)) == pcd.PCD_ERR_INVALID
+    assert L.pcd_slab_load_device(null, null, null) == pcd.PCD_ERR_INVALID
+    assert L.pcd_slab_store_device(null, null) == pcd.PCD_ERR_INVALID
+    assert L.pcd_slab_pass(null, 2, 0) == pcd.PCD_ERR_INVALID
+    assert L.pcd_slab_peer_handle_bytes() == 128
+    assert L.pcd_slab_ghost_rows() == 2 * L.pcd_slab_sweeps_per_pass() + 1
+    out = ctypes.c_void_p()
+    assert L.pcd_slab_create(16, 16, 8, 16, 0, None, ctypes.byref(out)) == pcd.PCD_ERR_INVALID   # rows beyond the grid
+    assert b"not a valid slab" in ctypes.c_char_p(L.pcd_last_error()).value

@@ -151,3 +151,31 @@ def test_full_size_properties_1024(pcd):
     s2.run(info["sweeps"], 0.0)
     assert np.array_equal(s2.download(), phi)
     s2.close()
+
+
+def test_full_size_properties_8192(pcd):
+    """BASELINE.json configs[4] size (no CPU solve possible): the wavefront kernel equals the per-colour kernels bit
+    for bit after the same number of sweeps (odd count: exercises the single-sweep pass), and the solve is exactly
+    linear under scaling by a power of two (every operation of the update scales exactly)."""
+    n = 8192
+    rng = np.random.RandomState(5)
+    D = rng.standard_normal((n, n))
+    D -= D.mean()
+    phi0 = rng.standard_normal((n, n))
+    s = pcd.Solver(n, n, 0, pcd.SOLVER_AUTO)
+    assert s.path == "tiled"
+    s.upload(D, phi0)
+    info = s.run(7, 0.0)
+    a = s.download()
+    s.upload(4.0 * D, 4.0 * phi0)
+    info4 = s.run(7, 0.0)
+    a4 = s.download()
+    s.close()
+    assert info["sweeps"] == 7 and info4["last_max_update"] == 4.0 * info["last_max_update"]
+    assert np.array_equal(a4, 4.0 * a)
+    s2 = pcd.Solver(n, n, 0, pcd.SOLVER_STREAMING)
+    s2.upload(D, phi0)
+    info2 = s2.run(7, 0.0)
+    assert np.array_equal(s2.download(), a)
+    assert info2["last_max_update"] == info["last_max_update"]
+    s2.close()
