@@ -73,6 +73,7 @@ struct pcd_solver {
     double *halo = nullptr;         // device: boundary-row exchange buffers
     double *phi_alt = nullptr;      // device: ping-pong partner of phi on the tiled path
     int res_ctas = 0, res_threads = 0, res_rows_per_cta = 0, res_n_big = 0;
+    int res_pairs = 0;   // CTA-pair (cluster) launch of the resident kernel: 0 undecided, 1 in use, -1 not available
     size_t res_smem = 0;
     int sm_count = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;

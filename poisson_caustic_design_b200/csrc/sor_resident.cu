@@ -20,6 +20,10 @@
 // Threads whose strip touches NaN holes, phantom cells (odd W, short last slab) run a per-cell masked path.
 //
 // Update formula, ordering and stopping rule: src/solver.cpp:12-61,70-147 (see sor_kernels.cu header).
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "sor_common.cuh"
 
 namespace pcd {
@@ -43,18 +47,20 @@ struct ResParams {
     unsigned long long *g_max;   // [max_it] per-sweep max|delta| bit patterns
     unsigned long long *g_slot;  // [max_it] low 32: CTAs arrived, high 32: CTAs whose max >= tol
     ResState *state;
+    int pair;                 // 1: launched as clusters of two CTAs; the link inside a pair goes through DSMEM
 };
 
+// (generic addressing: a slot is either in global memory or -- inside a CTA pair -- in the partner's shared memory)
 __device__ __forceinline__ void ll_store(uint4 *p, double v, unsigned seq) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"(seq),
+    asm volatile("st.volatile.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"(seq),
                  "r"((unsigned)(b >> 32)), "r"(seq)
                  : "memory");
 }
 
 __device__ __forceinline__ uint4 ll_issue(const uint4 *p) {
     uint4 r;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    asm volatile("ld.volatile.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
     return r;
 }
 
@@ -197,6 +203,11 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
     const bool has_up = cta > 0, has_dn = cta + 1 < p.P;
 
     for (int i = tid; i < NR * 2 * Kp; i += RES_NT) smem[i] = 0.0;
+    // CTA pairs (clusters of two): the slots of the link INSIDE the pair live in shared memory behind the strip arrays
+    // (same offset in both CTAs); the partner writes them through DSMEM and this CTA polls its own shared memory
+    uint4 *pslot = reinterpret_cast<uint4 *>(smem + p.nr_big * 2 * Kp);
+    if (p.pair)
+        for (int i = tid; i < W; i += RES_NT) pslot[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) { blkmax[0] = 0ull; blkmax[1] = 0ull; s_stop = 0; }
     __syncthreads();
 
@@ -245,6 +256,14 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
     uint4 *ll_dn = has_dn ? p.ll + ((size_t)(cta + 1) * 2 + 0) * W : nullptr;   // neighbour below: its "from above" slots
     const uint4 *in_top = p.ll + ((size_t)cta * 2 + 0) * W;
     const uint4 *in_bot = p.ll + ((size_t)cta * 2 + 1) * W;
+    if (p.pair) {
+        cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+        if ((cta & 1) == 0) {          // partner = the CTA below
+            if (has_dn) { ll_dn = cl.map_shared_rank(pslot, 1); in_bot = pslot; }
+        } else {                        // partner = the CTA above
+            ll_up = cl.map_shared_rank(pslot, 0); in_top = pslot;
+        }
+    }
     if (idle) { ll_up = nullptr; ll_dn = nullptr; }
     double *smk = smem + 1 + k;
 
@@ -257,6 +276,7 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
         if (has_dn && !idle && xb < W) hd = p.phi[(size_t)(r0 + NR) * W + xb];
     }
     __syncthreads();
+    if (p.pair) cooperative_groups::this_cluster().sync();   // the partner's slots are zeroed before anything is sent
 
     const int max_it = p.max_it;
     int sweep = 0, conv_at = 0;
@@ -318,6 +338,7 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
         if (s_stop == sweep + 1 || sweep + 1 >= max_it) break;
     }
 
+    if (p.pair) cooperative_groups::this_cluster().sync();   // no CTA leaves while its partner may still store into it
     // ---- write the strip back ---------------------------------------------------------------------
 #pragma unroll
     for (int j = 0; j < NR; ++j)
@@ -333,9 +354,12 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
 template <int NR>
 __global__ void __launch_bounds__(RES_NT, 1) sor_resident_kernel(const __grid_constant__ ResParams p) {
     // the first and the last slab carry the domain's top / bottom row (different neighbour counts)
-    const bool edge = blockIdx.x == 0 || blockIdx.x + 1 == gridDim.x;
     const int c = (int)blockIdx.x;
-    if (c < p.n_big) {
+    const bool edge = c == 0 || c + 1 == p.P;
+    if (c >= p.P) {  // padding CTA of the last pair: only keeps the cluster barriers balanced
+        cooperative_groups::this_cluster().sync();
+        cooperative_groups::this_cluster().sync();
+    } else if (c < p.n_big) {
         if (edge) res_body<NR, true>(p, c * NR);
         else res_body<NR, false>(p, c * NR);
     } else if constexpr (NR >= 2) {  // slabs one row shorter: every slab is full, every CTA stays on the fast path
@@ -363,7 +387,7 @@ int resident_plan(pcd_solver *s) {
     const int Kp = RES_KP;
     s->res_ctas = P;
     s->res_rows_per_cta = pick;
-    s->res_smem = (size_t)pick * 2 * Kp * sizeof(double);
+    s->res_smem = (size_t)pick * 2 * Kp * sizeof(double) + (size_t)W * sizeof(uint4);  // + pair-link slots
     s->res_threads = RES_NT;
     return 1;
 }
@@ -371,6 +395,33 @@ int resident_plan(pcd_solver *s) {
 template <int NR>
 static int launch_resident(pcd_solver *s, ResParams &prm) {
     PCD_CUDA(cudaFuncSetAttribute(sor_resident_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->res_smem));
+    // preferred: clusters of two CTAs (one TPC), co-resident by cooperative launch; the link inside a pair then runs
+    // over DSMEM and only every other link crosses L2.  Falls back to the plain cooperative launch when the device
+    // cannot hold all pairs at once.
+    static const bool no_pairs = getenv("PCD_RES_NO_PAIRS") != nullptr;
+    if (s->res_pairs >= 0 && !no_pairs && s->res_ctas >= 2) {
+        const int grid = (s->res_ctas + 1) & ~1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(RES_NT); cfg.dynamicSmemBytes = s->res_smem; cfg.stream = s->stream;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 2;
+        if (s->res_pairs == 0) {   // decide once per solver
+            int n = 0;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, sor_resident_kernel<NR>, &cfg);
+            s->res_pairs = (e == cudaSuccess && n * 2 >= grid) ? 1 : -1;
+            if (e != cudaSuccess) cudaGetLastError();
+        }
+        if (s->res_pairs == 1) {
+            prm.pair = 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, sor_resident_kernel<NR>, prm);
+            if (e == cudaSuccess) { PCD_LAUNCHED(); return PCD_OK; }
+            cudaGetLastError();
+            s->res_pairs = -1;
+        }
+    }
+    prm.pair = 0;
     void *args[] = {&prm};
     PCD_CUDA(cudaLaunchCooperativeKernel((void *)sor_resident_kernel<NR>, dim3(s->res_ctas), dim3(RES_NT), args,
                                          s->res_smem, s->stream));
