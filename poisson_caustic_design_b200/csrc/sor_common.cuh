@@ -35,7 +35,8 @@ constexpr int RES_MAX_SWEEPS_PER_LAUNCH = 1 << 17;
 struct ResState {  // device control block of the resident kernel (mirrored in pinned host memory)
     int sweeps;
     int converged_at;
-    int pad0, pad1;
+    int error;   // a CTA gave up waiting for a neighbour (CTAs not co-resident): the launch is void, phi untouched
+    int done;    // CTAs that finished their sweeps; phi is written back only after all of them have
 };
 
 // sor_resident.cu

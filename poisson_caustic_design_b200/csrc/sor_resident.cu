@@ -64,8 +64,21 @@ __device__ __forceinline__ uint4 ll_issue(const uint4 *p) {
     return r;
 }
 
-__device__ __forceinline__ double ll_consume(uint4 r, const uint4 *p, unsigned seq) {
-    while (r.y != seq || r.w != seq) r = ll_issue(p);
+// A neighbour that never shows up (the pair launch is not cooperative: CTAs might not all be resident) must not hang
+// the GPU: after ~1 s of re-polling the launch is declared void (ResState::error) and every CTA bails out.
+constexpr unsigned RES_SPIN_CHECK = 1023u, RES_SPIN_LIMIT = 1u << 21;
+__device__ __forceinline__ bool res_give_up(unsigned &spins, int *err) {
+    if ((++spins & RES_SPIN_CHECK) != 0u) return false;
+    if (spins >= RES_SPIN_LIMIT) atomicExch(err, 1);
+    return *((volatile int *)err) != 0;
+}
+
+__device__ __forceinline__ double ll_consume(uint4 r, const uint4 *p, unsigned seq, int *err) {
+    unsigned spins = 0u;
+    while (r.y != seq || r.w != seq) {
+        r = ll_issue(p);
+        if (res_give_up(spins, err)) break;
+    }
     return __longlong_as_double((long long)(((unsigned long long)r.z << 32) | r.x));
 }
 
@@ -172,8 +185,8 @@ __device__ __forceinline__ void res_phase(Strip<NR> &s, double *__restrict__ smk
     InteriorRows<NR, P0, FAST, EDGE, 1>::load(smk, nb);
     InteriorRows<NR, P0, FAST, EDGE, 1>::compute(s, nb, ok, p, lmax);
     InteriorRows<NR, P0, FAST, EDGE, 1>::store(s, smk, ok);
-    if (pt) hu = ll_consume(rt, pt, seq - 1u);
-    if (pb) hd = ll_consume(rb, pb, seq - 1u);
+    if (pt) hu = ll_consume(rt, pt, seq - 1u, &p.state->error);
+    if (pb) hd = ll_consume(rb, pb, seq - 1u, &p.state->error);
     constexpr int q0 = P0 & 1, qb = (P0 + NR - 1) & 1;
     const bool ok0 = res_cell<NR, P0, FAST, EDGE, 0>(s, nb[0], hu, hd, p, lmax);
     bool okb = false;
@@ -284,7 +297,11 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
         double lmax = 0.0;
         unsigned long long pend = 0ull;
         const int e = sweep - p.lag;
-        if (tid == 0 && e >= 0) pend = *((const volatile unsigned long long *)(p.g_slot + e));  // consumed at the end of the sweep
+        int errv = 0;
+        if (tid == 0) {  // both consumed at the end of the sweep
+            if (e >= 0) pend = *((const volatile unsigned long long *)(p.g_slot + e));
+            errv = *((volatile int *)&p.state->error);
+        }
         int not_below = 0;
 #pragma unroll
         for (int colour = 0; colour < 2; ++colour) {
@@ -307,13 +324,18 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
             if (colour == 0) {
                 __syncthreads();
             } else {
-                if (tid == 0 && e >= 0 && conv_at == 0) {
-                    while ((unsigned)pend != (unsigned)p.P) pend = *((const volatile unsigned long long *)(p.g_slot + e));
-                    if ((pend >> 32) == 0ull) {
+                if (tid == 0 && e >= 0 && conv_at == 0 && !errv) {
+                    unsigned spins = 0u;
+                    while ((unsigned)pend != (unsigned)p.P) {
+                        pend = *((const volatile unsigned long long *)(p.g_slot + e));
+                        if (res_give_up(spins, &p.state->error)) { errv = 1; break; }
+                    }
+                    if (!errv && (pend >> 32) == 0ull) {
                         conv_at = e + 1;
                         s_stop = sweep + 1;
                     }
                 }
+                if (tid == 0 && errv) s_stop = sweep + 1;
                 // the barrier that ends the sweep also carries the CTA's verdict: is any |delta| of this sweep >= tol ?
                 not_below = __syncthreads_or(lmax >= p.tol);
             }
@@ -339,7 +361,20 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
     }
 
     if (p.pair) cooperative_groups::this_cluster().sync();   // no CTA leaves while its partner may still store into it
-    // ---- write the strip back ---------------------------------------------------------------------
+    // ---- write the strip back: only after EVERY CTA has finished its sweeps, and not when the launch was declared
+    // void -- so the input field is intact whenever the host has to repeat the launch --------------------------------
+    if (tid == 0) {
+        int ok = *((volatile int *)&p.state->error) == 0;
+        if (ok) {
+            atomicAdd(&p.state->done, 1);
+            unsigned spins = 0u;
+            while (*((volatile int *)&p.state->done) != p.P)
+                if (res_give_up(spins, &p.state->error)) { ok = 0; break; }
+        }
+        s_stop = ok ? -1 : -2;
+    }
+    __syncthreads();
+    if (s_stop != -1) return;
 #pragma unroll
     for (int j = 0; j < NR; ++j)
 #pragma unroll
@@ -395,18 +430,19 @@ int resident_plan(pcd_solver *s) {
 template <int NR>
 static int launch_resident(pcd_solver *s, ResParams &prm) {
     PCD_CUDA(cudaFuncSetAttribute(sor_resident_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->res_smem));
-    // preferred: clusters of two CTAs (one TPC), co-resident by cooperative launch; the link inside a pair then runs
-    // over DSMEM and only every other link crosses L2.  Falls back to the plain cooperative launch when the device
-    // cannot hold all pairs at once.
+    // preferred: clusters of two CTAs (one TPC each); the link inside a pair then runs over DSMEM and only every other
+    // link crosses L2.  This launch carries the cluster attribute only (cluster + cooperative is refused under the
+    // profiler): with one CTA per SM and at most one CTA per SM in the grid all pairs are resident on an idle device,
+    // which cudaOccupancyMaxActiveClusters confirms up front; should they ever not be, the kernel gives up after ~1 s
+    // (ResState::error), leaves phi untouched, and run_resident repeats the launch the cooperative way.
     static const bool no_pairs = getenv("PCD_RES_NO_PAIRS") != nullptr;
     if (s->res_pairs >= 0 && !no_pairs && s->res_ctas >= 2) {
         const int grid = (s->res_ctas + 1) & ~1;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(RES_NT); cfg.dynamicSmemBytes = s->res_smem; cfg.stream = s->stream;
-        cudaLaunchAttribute at[2];
+        cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
-        cfg.attrs = at; cfg.numAttrs = 2;
+        cfg.attrs = at; cfg.numAttrs = 1;
         if (s->res_pairs == 0) {   // decide once per solver
             int n = 0;
             cudaError_t e = cudaOccupancyMaxActiveClusters(&n, sor_resident_kernel<NR>, &cfg);
@@ -442,6 +478,7 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
         PCD_CUDA(cudaMemsetAsync(g_max, 0, sizeof(unsigned long long) * (size_t)k, s->stream));
         PCD_CUDA(cudaMemsetAsync(g_slot, 0, sizeof(unsigned long long) * (size_t)k, s->stream));
         PCD_CUDA(cudaMemsetAsync(s->halo, 0, (size_t)P * 2 * W * sizeof(uint4), s->stream));
+        PCD_CUDA(cudaMemsetAsync(s->res_state, 0, sizeof(ResState), s->stream));
         ResParams prm;
         prm.phi = phi; prm.D = D; prm.W = W; prm.H = H; prm.K = (W + 1) / 2;
         prm.Kp = RES_KP;
@@ -464,6 +501,11 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
         PCD_CUDA(cudaMemcpyAsync(s->h_res_state, s->res_state, sizeof(ResState), cudaMemcpyDeviceToHost, s->stream));
         PCD_CUDA(cudaStreamSynchronize(s->stream));
         const ResState st = *(ResState *)s->h_res_state;
+        if (st.error) {  // a CTA waited in vain: phi is untouched
+            if (s->res_pairs == 1) { s->res_pairs = -1; continue; }   // once more, cooperatively
+            set_error("resident K-SOR kernel: a CTA gave up waiting for its neighbour");
+            return PCD_ERR_CUDA;
+        }
         {
             float kms = 0.f;
             PCD_CUDA(cudaEventElapsedTime(&kms, s->evk0, s->evk1));
