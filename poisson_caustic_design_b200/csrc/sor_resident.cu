@@ -47,7 +47,7 @@ struct ResParams {
     unsigned long long *g_max;   // [max_it] per-sweep max|delta| bit patterns
     unsigned long long *g_slot;  // [max_it] low 32: CTAs arrived, high 32: CTAs whose max >= tol
     ResState *state;
-    int pair;                 // 1: launched as clusters of two CTAs; the link inside a pair goes through DSMEM
+    int pair;                 // cluster size of the launch (0: none): links inside a cluster go through DSMEM
 };
 
 // (generic addressing: a slot is either in global memory or -- inside a CTA pair -- in the partner's shared memory)
@@ -218,9 +218,9 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
     for (int i = tid; i < NR * 2 * Kp; i += RES_NT) smem[i] = 0.0;
     // CTA pairs (clusters of two): the slots of the link INSIDE the pair live in shared memory behind the strip arrays
     // (same offset in both CTAs); the partner writes them through DSMEM and this CTA polls its own shared memory
-    uint4 *pslot = reinterpret_cast<uint4 *>(smem + p.nr_big * 2 * Kp);
+    uint4 *pslot = reinterpret_cast<uint4 *>(smem + p.nr_big * 2 * Kp);   // [2][W]: from the CTA above / from below
     if (p.pair)
-        for (int i = tid; i < W; i += RES_NT) pslot[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < 2 * W; i += RES_NT) pslot[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) { blkmax[0] = 0ull; blkmax[1] = 0ull; s_stop = 0; }
     __syncthreads();
 
@@ -271,10 +271,12 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
     const uint4 *in_bot = p.ll + ((size_t)cta * 2 + 1) * W;
     if (p.pair) {
         cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
-        if ((cta & 1) == 0) {          // partner = the CTA below
-            if (has_dn) { ll_dn = cl.map_shared_rank(pslot, 1); in_bot = pslot; }
-        } else {                        // partner = the CTA above
-            ll_up = cl.map_shared_rank(pslot, 0); in_top = pslot;
+        const int rank = cta % p.pair;
+        if (rank != 0) {                          // the CTA above is in this cluster: its "from below" slots, my "from above"
+            ll_up = cl.map_shared_rank(pslot + W, rank - 1); in_top = pslot;
+        }
+        if (rank != p.pair - 1 && has_dn) {       // the CTA below is in this cluster
+            ll_dn = cl.map_shared_rank(pslot, rank + 1); in_bot = pslot + W;
         }
     }
     if (idle) { ll_up = nullptr; ll_dn = nullptr; }
@@ -422,7 +424,7 @@ int resident_plan(pcd_solver *s) {
     const int Kp = RES_KP;
     s->res_ctas = P;
     s->res_rows_per_cta = pick;
-    s->res_smem = (size_t)pick * 2 * Kp * sizeof(double) + (size_t)W * sizeof(uint4);  // + pair-link slots
+    s->res_smem = (size_t)pick * 2 * Kp * sizeof(double) + (size_t)2 * W * sizeof(uint4);  // + slots of the links inside a cluster
     s->res_threads = RES_NT;
     return 1;
 }
@@ -436,21 +438,23 @@ static int launch_resident(pcd_solver *s, ResParams &prm) {
     // which cudaOccupancyMaxActiveClusters confirms up front; should they ever not be, the kernel gives up after ~1 s
     // (ResState::error), leaves phi untouched, and run_resident repeats the launch the cooperative way.
     static const bool no_pairs = getenv("PCD_RES_NO_PAIRS") != nullptr;
+    static const int cs_env = getenv("PCD_RES_CLUSTER") ? atoi(getenv("PCD_RES_CLUSTER")) : 2;   // tuning knob
+    const int cs = (cs_env == 4 || cs_env == 8) ? cs_env : 2;
     if (s->res_pairs >= 0 && !no_pairs && s->res_ctas >= 2) {
-        const int grid = (s->res_ctas + 1) & ~1;
+        const int grid = (s->res_ctas + cs - 1) / cs * cs;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(RES_NT); cfg.dynamicSmemBytes = s->res_smem; cfg.stream = s->stream;
         cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         if (s->res_pairs == 0) {   // decide once per solver
             int n = 0;
             cudaError_t e = cudaOccupancyMaxActiveClusters(&n, sor_resident_kernel<NR>, &cfg);
-            s->res_pairs = (e == cudaSuccess && n * 2 >= grid) ? 1 : -1;
+            s->res_pairs = (e == cudaSuccess && n * cs >= grid) ? 1 : -1;
             if (e != cudaSuccess) cudaGetLastError();
         }
         if (s->res_pairs == 1) {
-            prm.pair = 1;
+            prm.pair = cs;
             cudaError_t e = cudaLaunchKernelEx(&cfg, sor_resident_kernel<NR>, prm);
             if (e == cudaSuccess) { PCD_LAUNCHED(); return PCD_OK; }
             cudaGetLastError();
