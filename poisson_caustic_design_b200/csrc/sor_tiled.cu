@@ -26,7 +26,11 @@
 
 namespace pcd {
 
-constexpr int WAVE_NT = 256;  // threads = column pairs per strip window
+#ifndef PCD_WAVE_NT
+#define PCD_WAVE_NT 256
+#endif
+constexpr int WAVE_NT = PCD_WAVE_NT;      // threads = column pairs per strip window
+constexpr int WAVE_CTAS = 512 / WAVE_NT;   // CTAs per SM (128 registers per thread)
 constexpr int WAVE_PF = 3;    // rows prefetched ahead by cp.async
 
 template <int TS>
@@ -205,7 +209,7 @@ struct WaveUnroll {
 };
 
 template <int TS, bool PEER>
-__global__ void __launch_bounds__(WAVE_NT, 2) sor_wave_kernel(const __grid_constant__ WaveParams p) {
+__global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __grid_constant__ WaveParams p) {
     using Cfg = WaveCfg<TS>;
     constexpr int R = Cfg::R, NP = Cfg::NP, PITCH = Cfg::PITCH;
     extern __shared__ double smem[];
@@ -340,7 +344,7 @@ static int launch_wave(const WaveParams &prm, int sm_count, cudaStream_t stream)
     // still fit one wave win even though the 2*NP warm-up rows are then a larger share of the work
     // (multi-GPU runs keep a few SMs free so that the NCCL kernels of the overlapped ghost-row exchange can run)
     const int avail = (sm_count - g_sm_reserve >= 8) ? sm_count - g_sm_reserve : sm_count;
-    int chunks = (2 * avail) / strips;
+    int chunks = (WAVE_CTAS * avail) / strips;
     int min_rows = 4 * Cfg::NP;  // a step costs the same latency whatever the chunk length: fill the wave first
     static const int dbg_chunks = getenv("PCD_WAVE_CHUNKS") ? atoi(getenv("PCD_WAVE_CHUNKS")) : 0;  // tuning knob
     if (dbg_chunks > 0) { chunks = dbg_chunks; min_rows = 8; }
