@@ -324,7 +324,12 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
                 }
             }
             if (colour == 0) {
-                __syncthreads();
+                // Between the two colours a warp only depends on its two neighbouring warps (the left / right cells of
+                // its first and last lane): two rounds of pairwise named barriers (pairs (0,1),(2,3).. then (1,2),(3,4)..)
+                // instead of a CTA-wide barrier, so a warp whose halo message is late holds up two warps, not sixteen.
+                const int wp = tid >> 5;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + (wp & ~1)) : "memory");
+                if (wp >= 1 && wp <= RES_NT / 32 - 2) asm volatile("bar.sync %0, 64;" ::"r"((wp & 1) ? 1 + wp : wp) : "memory");
             } else {
                 if (tid == 0 && e >= 0 && conv_at == 0 && !errv) {
                     unsigned spins = 0u;
