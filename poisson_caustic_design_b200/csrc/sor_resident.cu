@@ -66,6 +66,7 @@ __device__ __forceinline__ uint4 ll_issue(const uint4 *p) {
 
 // A neighbour that never shows up (the pair launch is not cooperative: CTAs might not all be resident) must not hang
 // the GPU: after ~1 s of re-polling the launch is declared void (ResState::error) and every CTA bails out.
+constexpr int RES_STOP_AHEAD = 10;   // sweeps between the stop decision and the stop (> the warps' maximum drift of 7.5 sweeps)
 constexpr unsigned RES_SPIN_CHECK = 1023u, RES_SPIN_LIMIT = 1u << 21;
 __device__ __forceinline__ bool res_give_up(unsigned &spins, int *err) {
     if ((++spins & RES_SPIN_CHECK) != 0u) return false;
@@ -207,7 +208,7 @@ __device__ __forceinline__ void res_phase(Strip<NR> &s, double *__restrict__ smk
 template <int NR, bool EDGE>
 __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
     extern __shared__ double smem[];  // [NR][2][Kp], element (j, q, k) at (j*2+q)*Kp + 1 + k; pads stay 0.0
-    __shared__ unsigned long long blkmax[2];
+    __shared__ unsigned arrive[16];   // per sweep (ring): low half = warps done, high half = warps with a |delta| >= tol
     __shared__ int s_stop;
 
     const int tid = threadIdx.x, cta = blockIdx.x, k = tid;
@@ -221,7 +222,8 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
     uint4 *pslot = reinterpret_cast<uint4 *>(smem + p.nr_big * 2 * Kp);   // [2][W]: from the CTA above / from below
     if (p.pair)
         for (int i = tid; i < 2 * W; i += RES_NT) pslot[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 0) { blkmax[0] = 0ull; blkmax[1] = 0ull; s_stop = 0; }
+    if (tid < 16) arrive[tid] = 0u;
+    if (tid == 0) s_stop = 0;
     __syncthreads();
 
     // ---- load the strip -----------------------------------------------------------------------
@@ -304,7 +306,6 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
             if (e >= 0) pend = *((const volatile unsigned long long *)(p.g_slot + e));
             errv = *((volatile int *)&p.state->error);
         }
-        int not_below = 0;
 #pragma unroll
         for (int colour = 0; colour < 2; ++colour) {
             const unsigned seq = 2u * (unsigned)sweep + (unsigned)colour + 1u;
@@ -323,48 +324,48 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
                     else res_phase<NR, 1, false, EDGE>(s, smk, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
                 }
             }
-            if (colour == 0) {
-                // Between the two colours a warp only depends on its two neighbouring warps (the left / right cells of
-                // its first and last lane): two rounds of pairwise named barriers (pairs (0,1),(2,3).. then (1,2),(3,4)..)
-                // instead of a CTA-wide barrier, so a warp whose halo message is late holds up two warps, not sixteen.
-                const int wp = tid >> 5;
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + (wp & ~1)) : "memory");
-                if (wp >= 1 && wp <= RES_NT / 32 - 2) asm volatile("bar.sync %0, 64;" ::"r"((wp & 1) ? 1 + wp : wp) : "memory");
-            } else {
-                if (tid == 0 && e >= 0 && conv_at == 0 && !errv) {
+            if (colour == 1 && tid == 0) {   // convergence duty: the verdict on sweep e = sweep - lag
+                if (e >= 0 && conv_at == 0 && !errv) {
                     unsigned spins = 0u;
                     while ((unsigned)pend != (unsigned)p.P) {
                         pend = *((const volatile unsigned long long *)(p.g_slot + e));
                         if (res_give_up(spins, &p.state->error)) { errv = 1; break; }
                     }
-                    if (!errv && (pend >> 32) == 0ull) {
-                        conv_at = e + 1;
-                        s_stop = sweep + 1;
-                    }
+                    if (!errv && (pend >> 32) == 0ull) conv_at = e + 1;
                 }
-                if (tid == 0 && errv) s_stop = sweep + 1;
-                // the barrier that ends the sweep also carries the CTA's verdict: is any |delta| of this sweep >= tol ?
-                not_below = __syncthreads_or(lmax >= p.tol);
+                // the warps of a CTA drift apart by up to 15 phases (below): the stop is announced RES_STOP_AHEAD sweeps
+                // ahead so that every warp of every CTA leaves after the same sweep
+                if ((conv_at == e + 1 && e >= 0) || errv) *((volatile int *)&s_stop) = sweep + 1 + RES_STOP_AHEAD;
+            }
+            // After a phase a warp only depends on its two neighbouring warps (the left / right cells of its first and
+            // last lane): two rounds of pairwise named barriers (pairs (0,1),(2,3).. then (1,2),(3,4)..) instead of a
+            // CTA-wide barrier, so a warp whose halo message is late holds up two warps, not sixteen.
+            {
+                const int wp = tid >> 5;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + (wp & ~1)) : "memory");
+                if (wp >= 1 && wp <= RES_NT / 32 - 2) asm volatile("bar.sync %0, 64;" ::"r"((wp & 1) ? 1 + wp : wp) : "memory");
             }
         }
-        // The per-sweep maximum itself is only ever read for sweeps at which every CTA is below tol (the sweep the solve
-        // stops at) and for the last sweeps of a launch that hits its cap (the host scans those): reduce it only then.
-        const bool need_max = !not_below || sweep + p.lag + 3 >= max_it;
-        if (need_max) {
-            const double wm = warp_max(lmax);
-            if ((tid & 31) == 0 && wm > 0.0) atomicMax(&blkmax[0], (unsigned long long)__double_as_longlong(wm));
-            __syncthreads();
-        }
-        // publish this sweep: arrival + verdict in one atomic
-        if (tid == 0) {
-            atomicAdd(p.g_slot + sweep, 1ull | (not_below ? (1ull << 32) : 0ull));
-            if (need_max) {
-                const unsigned long long bm = blkmax[0];
-                blkmax[0] = 0ull;
-                if (bm) atomicMax(p.g_max + sweep, bm);
+        // End of the sweep, per WARP (no CTA-wide barrier): the warp's verdict goes into this sweep's arrival word; the
+        // last warp to arrive publishes the CTA's arrival + verdict with one atomic.  The maximum itself is only ever
+        // read for sweeps at which every warp is below tol (the sweep the solve stops at) and for the last sweeps of a
+        // launch that hits its cap (the host scans those): reduce it only then.
+        {
+            const bool wany = __any_sync(0xffffffffu, lmax >= p.tol);
+            if (!wany || sweep + p.lag + 3 >= max_it) {
+                const double wm = warp_max(lmax);
+                if ((tid & 31) == 0 && wm > 0.0) atomicMax(p.g_max + sweep, (unsigned long long)__double_as_longlong(wm));
+            }
+            if ((tid & 31) == 0) {
+                const unsigned add = 1u | (wany ? 0x10000u : 0u);
+                const unsigned old = atomicAdd(&arrive[sweep & 15], add);
+                if ((old & 0xffffu) == RES_NT / 32 - 1) {
+                    arrive[sweep & 15] = 0u;   // next used 16 sweeps from now
+                    atomicAdd(p.g_slot + sweep, 1ull | (((old + add) >> 16) ? (1ull << 32) : 0ull));
+                }
             }
         }
-        if (s_stop == sweep + 1 || sweep + 1 >= max_it) break;
+        if (*((volatile int *)&s_stop) == sweep + 1 || sweep + 1 >= max_it) break;
     }
 
     if (p.pair) cooperative_groups::this_cluster().sync();   // no CTA leaves while its partner may still store into it
