@@ -1,23 +1,29 @@
-// K-SOR, resident path: ONE persistent cooperative kernel per Poisson solve (sm_100a).
+// K-SOR, resident path: ONE persistent kernel per Poisson solve (sm_100a), one CTA per SM, all CTAs co-resident.
 //
-// Decomposition: CTA c (one per SM, co-resident by cooperative launch) owns NR consecutive grid rows
-// [c*NR, c*NR+NR); thread k of its 512 threads owns the column pair (2k, 2k+1) of every one of those
-// rows -- a vertical strip of 2*NR cells whose phi and D values stay in REGISTERS for the whole solve.
+// Decomposition: the H rows are split as evenly as possible over P = ceil(H/NR) CTAs (slabs of NR and NR-1
+// rows); thread k of a CTA's 512 threads owns the column pair (2k, 2k+1) of every row of the slab -- a vertical
+// strip of 2*NR cells whose phi and D values stay in REGISTERS for the whole solve.
 //   * up / down neighbours of a cell are the thread's own registers (compile-time indices);
 //   * the left / right neighbour that belongs to thread k-1 / k+1 goes through shared memory
 //     (one STS + one LDS per cell update, unit stride, conflict-free);
 //   * the rows above / below the slab belong to the neighbouring CTAs: each boundary cell is pushed to
-//     the neighbour through L2 as one 16-byte flag-in-data message {lo, seq, hi, seq} ("LL" protocol:
-//     each 8-byte half is written atomically and carries the phase number, so the reader needs no
-//     fence and no separate flag) and is polled by exactly the thread that consumes it -> registers.
-//     There is no grid-wide barrier; CTAs only ever wait for their two neighbours.
-//   * convergence: per sweep every CTA adds (1 | not_converged<<32) to that sweep's slot with ONE
-//     atomic (arrival count and verdict travel together, no fence); the slot of sweep s-lag is read at
-//     the end of sweep s by thread 0 of every CTA, so all CTAs leave after the same sweep.
+//     the neighbour as one 16-byte flag-in-data message {lo, seq, hi, seq} ("LL" protocol: each 8-byte
+//     half is written atomically and carries the phase number, so the reader needs no fence and no
+//     separate flag) and is polled by exactly the thread that consumes it -> registers.  The kernel runs as
+//     clusters of two CTAs: the link inside a pair uses slots in the partner's shared memory (DSMEM), the
+//     other link slots in global memory (L2).  There is no grid-wide barrier; CTAs only wait for their
+//     two neighbours;
+//   * inside a CTA there is no CTA-wide barrier in the sweep loop either: after a phase a warp syncs with
+//     its two neighbouring warps only (pairwise named barriers);
+//   * convergence: per sweep every warp adds its verdict to the sweep's arrival word in shared memory, the
+//     last warp adds (1 | not_converged<<32) to that sweep's global slot with ONE atomic (arrival count and
+//     verdict travel together, no fence); the slot of sweep s-lag is read at the end of sweep s by thread
+//     0 of every CTA and the stop is announced RES_STOP_AHEAD sweeps ahead, so all warps of all CTAs leave
+//     after the same sweep.
 // Domain edges cost nothing in the hot loop: a missing neighbour reads a 0.0 ghost (x + 0.0 == x, so the
 // reference's "skip the neighbour" sum is reproduced bit for bit) and the per-cell neighbour count /
 // omega/cnt factors are per-thread registers selected at compile time by (row class, column parity).
-// Threads whose strip touches NaN holes, phantom cells (odd W, short last slab) run a per-cell masked path.
+// Threads whose strip touches NaN holes or phantom cells (odd W) run a per-cell masked path.
 //
 // Update formula, ordering and stopping rule: src/solver.cpp:12-61,70-147 (see sor_kernels.cu header).
 #include <cooperative_groups.h>
