@@ -280,6 +280,8 @@ def solve(engine, dist, rank: int, world: int, max_iterations: int, tol: float, 
         m_host = m.cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
         conv, last = _decide(m_host, tol, done)
         done += k
+    if overlap:
+        lib().pcd_slab_set_sm_reserve(0)   # process-wide setting: give the SMs back to later solves
     return {"sweeps": done, "converged_at": conv, "last_max_update": last, "mode": "wavefront" if wave else "colour"}
 
 
