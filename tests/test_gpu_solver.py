@@ -181,3 +181,34 @@ def test_full_size_properties_8192(pcd):
     assert np.array_equal(s2.download(), a)
     assert info2["last_max_update"] == info["last_max_update"]
     s2.close()
+
+
+@pytest.mark.parametrize("shape", [(1024, 1024), (1000, 1000), (777, 1024), (1024, 600), (333, 1000), (1024, 1023), (149, 1024),
+                                   (296, 64), (1036, 998)])
+def test_resident_kernel_at_production_sizes_bit_exact(pcd, shape):
+    """The on-chip kernel (CTA pairs over DSMEM, uneven row split, warp-level barriers, stop announced ahead) against the
+    per-colour kernels at sizes where all 148 CTAs and all 16 warps take part: same bits after 1, 2 and 37 sweeps and
+    after a run to convergence (same converged_at, same field for the same number of sweeps)."""
+    H, W = shape
+    rng = np.random.RandomState(H + W)
+    D = rng.standard_normal((H, W)) * 1e-3
+    D -= D.mean()
+    phi0 = rng.standard_normal((H, W))
+    r = pcd.Solver(W, H, 0, pcd.SOLVER_RESIDENT)
+    s = pcd.Solver(W, H, 0, pcd.SOLVER_STREAMING)
+    for n in (1, 2, 37):
+        r.upload(D, phi0)
+        s.upload(D, phi0)
+        ir, is_ = r.run(n, 0.0), s.run(n, 0.0)
+        assert ir["sweeps"] == n and np.array_equal(r.download(), s.download()), n
+        assert ir["last_max_update"] == is_["last_max_update"], n
+    z = np.zeros_like(D)
+    r.upload(D, z)
+    ir = r.run(100000, 1e-6)
+    assert 0 < ir["converged_at"] <= ir["sweeps"] <= ir["converged_at"] + 64
+    s.upload(D, z)
+    is_ = s.run(ir["sweeps"], 0.0)
+    assert np.array_equal(r.download(), s.download())
+    s.upload(D, z)
+    assert s.run(100000, 1e-6)["converged_at"] == ir["converged_at"]
+    r.close(); s.close()
