@@ -331,11 +331,15 @@ void tiled_set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : n; }
 template <int TS, bool PEER>
 static int launch_wave(const WaveParams &prm, int sm_count, cudaStream_t stream) {
     using Cfg = WaveCfg<TS>;
-    static bool attr_set = false;
     const size_t smem = (size_t)2 * Cfg::R * 2 * Cfg::PITCH * sizeof(double);
-    if (!attr_set) {
-        PCD_CUDA(cudaFuncSetAttribute(sor_wave_kernel<TS, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+    {   // the opt-in is per device: remember which devices have it
+        static unsigned long long done_mask = 0ull;
+        int dev = 0;
+        PCD_CUDA(cudaGetDevice(&dev));
+        if (dev >= 64 || !((done_mask >> dev) & 1ull)) {
+            PCD_CUDA(cudaFuncSetAttribute(sor_wave_kernel<TS, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev < 64) done_mask |= 1ull << dev;
+        }
     }
     WaveParams p = prm;
     const int strips = (p.W + Cfg::CORE - 1) / Cfg::CORE;
