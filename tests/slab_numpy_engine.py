@@ -82,3 +82,38 @@ class NumpySlabEngine:
 
     def download(self):
         return self.phi.numpy()[self.GH:self.GH + self.rows].copy()
+
+
+class NumpyPeerEngine(NumpySlabEngine):
+    """Adds the fused-exchange interface (peer_export / peer_connect_ipc / peer_run / peer_timed_out): `peer_run`
+    stands in for the pass kernels that push their ghost rows into the neighbour themselves -- here the push is a
+    gloo send/recv issued from inside the engine, so slab.solve's peer path (handle all-gather, agreement, block
+    structure, status check) runs on CPU."""
+
+    def __init__(self, W, H, row0, rows, dist, rank, world, fail_connect=False):
+        super().__init__(W, H, row0, rows)
+        self.dist, self.rank, self.world, self.fail_connect = dist, rank, world, fail_connect
+        self.neighbours = {}
+        self.runs = 0
+
+    def peer_export(self):
+        h = np.zeros(128, dtype=np.uint8)
+        h[:4] = np.frombuffer(np.int32(self.row0).tobytes(), dtype=np.uint8)   # something rank-specific to check
+        return h
+
+    def peer_connect_ipc(self, side, handles, peer_row0, peer_rows):
+        if self.fail_connect:
+            raise RuntimeError("cannot attach the neighbour")
+        assert int(np.frombuffer(np.asarray(handles, dtype=np.uint8)[:4].tobytes(), dtype=np.int32)[0]) == peer_row0
+        assert peer_row0 == (self.row0 - peer_rows if side == 0 else self.row0 + self.rows)
+        self.neighbours[side] = (peer_row0, peer_rows)
+
+    def peer_run(self, nsweeps, slot):
+        from poisson_caustic_design_b200 import slab
+        self.runs += 1
+        for j in range(0, nsweeps, self.TS):
+            self.pass_(min(self.TS, nsweeps - j), slot + j)
+            slab._exchange(self, self.dist, self.rank, self.world, self.GH)
+
+    def peer_timed_out(self):
+        return False

@@ -103,3 +103,46 @@ def test_gloo_slabs_stopping_rule(port, tmp_path):
     want = port.poisson_rb(D, z, 100000, 1e-7, extra_sweeps=int(info[0]) - conv_exact)[0]
     assert np.array_equal(phi, want)
     assert info[2] < 1e-7
+
+
+def _peer_worker(rank, world, port, D, phi0, max_it, tol, check_every, out_dir, failing_rank):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from poisson_caustic_design_b200 import slab
+    from slab_numpy_engine import NumpyPeerEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    H, W = D.shape
+    row0, rows = slab.partition(H, world, rank)
+    eng = NumpyPeerEngine(W, H, row0, rows, dist, rank, world, fail_connect=(rank == failing_rank))
+    eng.upload(slab.with_ghosts(D, row0, rows, eng.GH), slab.with_ghosts(phi0, row0, rows, eng.GH))
+    info = slab.solve(eng, dist, rank, world, max_it, tol, check_every)
+    if failing_rank < 0:
+        assert info["mode"] == "peer" and eng.runs == -(-info["sweeps"] // check_every)
+        assert set(eng.neighbours) == {s for s, nb in ((0, rank - 1), (1, rank + 1)) if 0 <= nb < world}
+    else:
+        assert info["mode"] == "wavefront" and eng.runs == 0        # every rank fell back, also the ones that attached fine
+    np.save(os.path.join(out_dir, f"phi_{rank}.npy"), eng.download())
+    np.save(os.path.join(out_dir, f"info_{rank}.npy"), np.array([info["sweeps"], info["converged_at"], info["last_max_update"]]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("failing_rank", [-1, 1])
+def test_gloo_peer_mode_host_logic(port, failing_rank, tmp_path):
+    """The fused-exchange path of slab.solve (handles all-gathered, neighbours attached, one peer_run per block of
+    sweeps, the only collective = the all-reduce of the maxima), and the agreement to fall back when ONE rank
+    cannot attach its neighbour."""
+    world = 3
+    rng = np.random.RandomState(77)
+    H, W = 47, 22                                      # slabs of 15/16 rows >= 2*GH
+    D = rng.standard_normal((H, W))
+    D -= D.mean()
+    phi0 = rng.standard_normal((H, W))
+    mp.spawn(_peer_worker, args=(world, 29680 + failing_rank, D, phi0, 21, 0.0, 8, str(tmp_path), failing_rank), nprocs=world, join=True)
+    phi = np.concatenate([np.load(tmp_path / f"phi_{r}.npy") for r in range(world)], axis=0)
+    infos = [np.load(tmp_path / f"info_{r}.npy") for r in range(world)]
+    for i in infos[1:]:
+        assert np.array_equal(i, infos[0])
+    want, n, conv, last = port.poisson_rb(D, phi0, 21, 0.0)
+    assert int(infos[0][0]) == 21 and np.array_equal(phi, want) and infos[0][2] == last
