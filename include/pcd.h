@@ -131,6 +131,14 @@ int pcd_flush_l2(pcd_ctx *ctx);
 typedef int (*pcd_solve_hook)(void *user, const double *D_dev, double *phi_dev, int width, int height, int max_iterations,
                               double tol, pcd_solve_info *info);
 int pcd_set_solve_hook(pcd_ctx *ctx, pcd_solve_hook hook, void *user);
+/* Stopping thresholds (max|delta| of a sweep) of the two Poisson solves; <= 0 keeps the current value.
+ * Defaults: transport 1e-7 = the reference's (src/caustic_design.cpp:222); height 1e-9, TIGHTER than the
+ * reference's 1e-8 (:311): at 1e-8 the reference's lexicographic sweeps and red-black sweeps stop on opposite
+ * sides of the converged discrete field (C1: 6.7e-5 and 7.3e-5 of the height range away from it, 1.4e-4 from
+ * each other); at 1e-9 the red-black result is 7e-6 from the converged field, i.e. the remaining distance to the
+ * reference is the reference's own truncation error (tests/test_oracle_golden.py::test_height_truncation_evidence).
+ * pcd_set_tolerances(ctx, 0, 1e-8) restores the reference's threshold. */
+int pcd_set_tolerances(pcd_ctx *ctx, double transport_tol, double height_tol);
 int pcd_stage_errors(pcd_ctx *ctx);                                       /* caustic_design.cpp:194-209 */
 int pcd_stage_raster(pcd_ctx *ctx);                                       /* :212-213, no mean removal */
 int pcd_stage_subtract_average(pcd_ctx *ctx);                             /* :221 */
@@ -148,8 +156,12 @@ int pcd_solver_create(int width, int height, int device, int solver_path, pcd_so
 void pcd_solver_destroy(pcd_solver *s);
 int pcd_solver_upload(pcd_solver *s, const double *D /* or NULL */, const double *phi /* or NULL */);
 int pcd_solver_download(pcd_solver *s, double *phi);
+/* the same with DEVICE arrays on the solver's device (device-to-device copies on the solver's stream; either
+ * argument of load may be NULL) */
+int pcd_solver_load_device(pcd_solver *s, const double *D_dev, const double *phi_dev);
+int pcd_solver_store_device(pcd_solver *s, double *phi_dev);
 /* check_lag: convergence of sweep s is acted on after sweep s+check_lag (resident path) or at the next
- * multiple of check_lag (streaming path); <= 0 selects the default.  The field is bit-identical to
+ * multiple of check_lag (streaming path); <= 0 selects the default, values above 4094 are clamped to 4094.  The field is bit-identical to
  * the red-black oracle run for `sweeps` sweeps. */
 int pcd_solver_set_check_lag(pcd_solver *s, int check_lag);
 int pcd_solver_run(pcd_solver *s, int max_iterations, double convergence_threshold, pcd_solve_info *info);
@@ -166,9 +178,9 @@ int pcd_solver_path_used(const pcd_solver *s);
 typedef struct pcd_slab pcd_slab;
 int pcd_slab_ghost_rows(void);
 int pcd_slab_sweeps_per_pass(void);
-void pcd_slab_set_sm_reserve(int n);   /* SMs the pass kernel leaves free for the collective's kernels (default 0) */
 int pcd_slab_create(int width, int height, int row0, int rows, int device, void *cuda_stream, pcd_slab **out);
 void pcd_slab_destroy(pcd_slab *s);
+int pcd_slab_set_sm_reserve(pcd_slab *s, int n);   /* SMs this slab's pass kernels leave free for the collective's kernels (default 0) */
 int pcd_slab_device_ptrs(pcd_slab *s, void **phi0_dev, void **phi1_dev, void **sweep_max_dev);
 int pcd_slab_current(const pcd_slab *s);   /* which of the two phi buffers holds the field */
 int pcd_slab_has_nan(const pcd_slab *s);   /* D (owned rows and their neighbours) contains NaN */
@@ -198,6 +210,11 @@ int pcd_slab_peer_connect_ipc(pcd_slab *s, int side, const unsigned char *handle
 int pcd_slab_peer_connect_local(pcd_slab *s, int side, pcd_slab *peer);
 int pcd_slab_peer_run(pcd_slab *s, int nsweeps, int slot);
 int pcd_slab_peer_status(pcd_slab *s, int *timed_out);
+/* asynchronous variant for the convergence block: copies the slab's error word (1 = a pass ran into the limit) into
+ * the DEVICE double *dst_dev on the slab's stream, so the host layer can fold it into the all-reduce of the maxima
+ * and every rank learns about a stalled neighbour in the same block.  The word is cleared by pcd_slab_upload /
+ * pcd_slab_load_device (a new solve starts clean). */
+int pcd_slab_peer_error_to(pcd_slab *s, double *dst_dev);
 
 #ifdef __cplusplus
 }

@@ -20,8 +20,9 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PCD_LIB") or os.path.join(PKG_DIR, "libpcd_b200.so")  # PCD_LIB: diagnostic builds only
 
 PCD_OK, PCD_ERR_INVALID, PCD_ERR_CUDA, PCD_ERR_NO_DEVICE, PCD_ERR_RASTER_MISS, PCD_ERR_STATE, PCD_ERR_UNSUPPORTED = range(7)
-SOLVER_AUTO, SOLVER_STREAMING, SOLVER_RESIDENT, SOLVER_TILED = 0, 1, 2, 3
-SOLVER_PATH_NAMES = {SOLVER_AUTO: "auto", SOLVER_STREAMING: "streaming", SOLVER_RESIDENT: "resident", SOLVER_TILED: "tiled"}
+SOLVER_AUTO, SOLVER_STREAMING, SOLVER_RESIDENT, SOLVER_TILED, SOLVER_DCT = 0, 1, 2, 3, 4
+SOLVER_PATH_NAMES = {SOLVER_AUTO: "auto", SOLVER_STREAMING: "streaming", SOLVER_RESIDENT: "resident", SOLVER_TILED: "tiled",
+                     SOLVER_DCT: "dct"}
 
 FIELDS = {
     "phi": 0, "h": 1, "raster": 2, "pixels": 3, "divergence": 4, "norm_x": 5, "norm_y": 6,
@@ -87,6 +88,8 @@ ABI = [
     ("pcd_solver_destroy", None, [C.c_void_p]),
     ("pcd_solver_upload", C.c_int, [C.c_void_p, _dp, _dp]),
     ("pcd_solver_download", C.c_int, [C.c_void_p, _dp]),
+    ("pcd_solver_load_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("pcd_solver_store_device", C.c_int, [C.c_void_p, C.c_void_p]),
     ("pcd_solver_set_check_lag", C.c_int, [C.c_void_p, C.c_int]),
     ("pcd_solver_run", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.POINTER(pcd_solve_info)]),
     ("pcd_solver_path_used", C.c_int, [C.c_void_p]),
@@ -99,7 +102,7 @@ ABI = [
     ("pcd_slab_pass", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("pcd_slab_pass_part", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("pcd_slab_flip", C.c_int, [C.c_void_p]),
-    ("pcd_slab_set_sm_reserve", None, [C.c_int]),
+    ("pcd_slab_set_sm_reserve", C.c_int, [C.c_void_p, C.c_int]),
     ("pcd_slab_ghost_rows", C.c_int, []),
     ("pcd_slab_sweeps_per_pass", C.c_int, []),
     ("pcd_slab_current", C.c_int, [C.c_void_p]),
@@ -108,12 +111,14 @@ ABI = [
     ("pcd_slab_load_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pcd_slab_store_device", C.c_int, [C.c_void_p, C.c_void_p]),
     ("pcd_set_solve_hook", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("pcd_set_tolerances", C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     ("pcd_slab_peer_handle_bytes", C.c_int, []),
     ("pcd_slab_peer_export", C.c_int, [C.c_void_p, C.c_void_p]),
     ("pcd_slab_peer_connect_ipc", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     ("pcd_slab_peer_connect_local", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("pcd_slab_peer_run", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("pcd_slab_peer_status", C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    ("pcd_slab_peer_error_to", C.c_int, [C.c_void_p, C.c_void_p]),
 ]
 
 
@@ -197,6 +202,13 @@ class Solver:
         _check(lib().pcd_solver_download(self._h, _p(out)))
         return out
 
+    def load_device(self, D_dev: int | None = None, phi_dev: int | None = None):
+        """D / phi from device arrays (raw pointers, e.g. ``tensor.data_ptr()``) on the solver's device."""
+        _check(lib().pcd_solver_load_device(self._h, C.c_void_p(D_dev) if D_dev else None, C.c_void_p(phi_dev) if phi_dev else None))
+
+    def store_device(self, phi_dev: int):
+        _check(lib().pcd_solver_store_device(self._h, C.c_void_p(phi_dev)))
+
     def set_check_lag(self, lag: int):
         _check(lib().pcd_solver_set_check_lag(self._h, lag))
 
@@ -264,6 +276,10 @@ class CausticDesign:
         upd = C.c_double(0.0)
         _check(lib().pcd_perform_height_map_iteration(self._h, itr, C.byref(upd)))
         return upd.value
+
+    def set_tolerances(self, transport_tol: float = 0.0, height_tol: float = 0.0):
+        """Stopping thresholds of the two Poisson solves (<= 0 keeps the current one); call after initialize_solvers."""
+        _check(lib().pcd_set_tolerances(self._h, float(transport_tol), float(height_tol)))
 
     def last_solve_info(self) -> dict:
         info = pcd_solve_info()

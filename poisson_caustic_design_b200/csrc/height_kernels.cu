@@ -97,7 +97,7 @@ int k_height_iteration(pcd_ctx *c, double *update_sum_host) {
     divergence_kernel<<<dim3((W + 127) / 128, H), 128, 0, st>>>(c->norm_x, c->norm_y, W, H, c->divergence);
     PCD_LAUNCHED();
     PCD_TRY(k_subtract_average(c, c->divergence));
-    PCD_TRY(ctx_solve(c, c->divergence, c->h, 0.00000001));  // :311
+    PCD_TRY(ctx_solve(c, c->divergence, c->h, c->height_tol));  // :311 (threshold: pcd_set_tolerances)
     const unsigned long long init_key = ~0ull;
     PCD_CUDA(cudaMemcpyAsync(c->d_bits + 2, &init_key, sizeof(init_key), cudaMemcpyHostToDevice, st));
     vertex_height_kernel<<<(V + 127) / 128, 128, 0, st>>>(c->h, c->sx, c->sy, V, W, H, c->cfg.width, c->cfg.height, c->hv,

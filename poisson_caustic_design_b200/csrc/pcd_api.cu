@@ -187,6 +187,13 @@ int pcd_set_solve_hook(pcd_ctx *ctx, pcd_solve_hook hook, void *user) {
     return PCD_OK;
 }
 
+int pcd_set_tolerances(pcd_ctx *ctx, double transport_tol, double height_tol) {
+    NEED_CTX(ctx);
+    if (transport_tol > 0.0) ctx->transport_tol = transport_tol;
+    if (height_tol > 0.0) ctx->height_tol = height_tol;
+    return PCD_OK;
+}
+
 int pcd_stage_errors(pcd_ctx *ctx) { NEED_INIT(ctx); return k_errors(ctx); }
 int pcd_stage_raster(pcd_ctx *ctx) {
     NEED_INIT(ctx);
@@ -196,7 +203,7 @@ int pcd_stage_raster(pcd_ctx *ctx) {
 int pcd_stage_subtract_average(pcd_ctx *ctx) { NEED_INIT(ctx); return k_subtract_average(ctx, ctx->raster); }
 int pcd_stage_solve_transport(pcd_ctx *ctx) {
     NEED_INIT(ctx);
-    return ctx_solve(ctx, ctx->raster, ctx->phi, 0.0000001);  // caustic_design.cpp:222
+    return ctx_solve(ctx, ctx->raster, ctx->phi, ctx->transport_tol);  // caustic_design.cpp:222
 }
 int pcd_stage_step(pcd_ctx *ctx, double *step_out) {
     NEED_INIT(ctx);
@@ -212,7 +219,7 @@ int pcd_perform_transport_iteration(pcd_ctx *ctx, double *step_out) {
     PCD_TRY(k_raster_target(ctx));
     PCD_TRY(check_miss(ctx, "target raster"));
     PCD_TRY(k_subtract_average(ctx, ctx->raster));
-    PCD_TRY(ctx_solve(ctx, ctx->raster, ctx->phi, 0.0000001));
+    PCD_TRY(ctx_solve(ctx, ctx->raster, ctx->phi, ctx->transport_tol));
     double s = 0.0;
     PCD_TRY(k_step(ctx, &s));
     if (step_out) *step_out = s;
@@ -282,6 +289,9 @@ int pcd_set_field(pcd_ctx *ctx, int field, const double *src) {
     if (n < 0 || !p) { set_error("field %d is not writable", field); return PCD_ERR_INVALID; }
     PCD_CUDA(cudaMemcpyAsync(p, src, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     PCD_CUDA(cudaStreamSynchronize(ctx->stream));
+    // the owner map of the source mesh is cached across height iterations (the reference never moves it): a caller
+    // that does move it gets a fresh map
+    if (field == PCD_FIELD_SOURCE_X || field == PCD_FIELD_SOURCE_Y) ctx->owner_src_valid = false;
     return PCD_OK;
 }
 
@@ -382,9 +392,28 @@ int pcd_solver_download(pcd_solver *s, double *phi) {
     return PCD_OK;
 }
 
+int pcd_solver_load_device(pcd_solver *s, const double *D_dev, const double *phi_dev) {
+    if (!s) { set_error("null solver"); return PCD_ERR_INVALID; }
+    PCD_TRY(select_device(s->device));
+    const size_t bytes = sizeof(double) * (size_t)s->W * s->H;
+    if (D_dev) PCD_CUDA(cudaMemcpyAsync(s->D, D_dev, bytes, cudaMemcpyDeviceToDevice, s->stream));
+    if (phi_dev) PCD_CUDA(cudaMemcpyAsync(s->phi, phi_dev, bytes, cudaMemcpyDeviceToDevice, s->stream));
+    PCD_CUDA(cudaStreamSynchronize(s->stream));
+    return PCD_OK;
+}
+
+int pcd_solver_store_device(pcd_solver *s, double *phi_dev) {
+    if (!s || !phi_dev) { set_error("null argument"); return PCD_ERR_INVALID; }
+    PCD_TRY(select_device(s->device));
+    PCD_CUDA(cudaMemcpyAsync(phi_dev, s->phi, sizeof(double) * (size_t)s->W * s->H, cudaMemcpyDeviceToDevice, s->stream));
+    PCD_CUDA(cudaStreamSynchronize(s->stream));
+    return PCD_OK;
+}
+
 int pcd_solver_set_check_lag(pcd_solver *s, int check_lag) {
     if (!s) { set_error("null solver"); return PCD_ERR_INVALID; }
-    s->check_lag = check_lag;
+    // the pinned mirror of the per-sweep maxima holds 4096 entries and the resident path reads lag + 2 of them
+    s->check_lag = check_lag < 0 ? 0 : (check_lag > 4094 ? 4094 : check_lag);
     return PCD_OK;
 }
 

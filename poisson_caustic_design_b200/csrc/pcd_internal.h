@@ -118,6 +118,8 @@ struct pcd_ctx {
     pcd_solve_info totals{};
     cudaEvent_t events[8] = {};
     void *l2_scratch = nullptr;
+    double transport_tol = 0.0000001;  // src/caustic_design.cpp:222
+    double height_tol = 1e-9;          // the reference uses 1e-8 (:311); see pcd_set_tolerances in pcd.h
     pcd_solve_hook solve_hook = nullptr;  // external Poisson solver (pcd_set_solve_hook)
     void *solve_hook_user = nullptr;
 };

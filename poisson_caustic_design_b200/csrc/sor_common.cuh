@@ -46,9 +46,9 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
 
 // sor_tiled.cu
 int tiled_sweeps_per_pass();
-void tiled_set_sm_reserve(int n);  // SMs left free by the wavefront kernel (overlapped multi-GPU exchange)
+// sm_count: SMs of the device the pass runs on; sm_reserve: SMs the pass leaves free (overlapped multi-GPU exchange)
 int tiled_pass(const double *phi_in, double *phi_out, const double *D, int W, int H, int row_first, int rows, int grow0,
-               int nsweeps, unsigned long long *slots, cudaStream_t stream);
+               int nsweeps, unsigned long long *slots, int sm_count, int sm_reserve, cudaStream_t stream);
 
 // Ghost-row exchange fused into the wavefront pass (multi-GPU slabs): the CTAs that finish the `gh` owned rows next to
 // a slab edge store them to the neighbour's output field as well (peer memory over NVLink) and the last of them
@@ -65,6 +65,7 @@ struct WavePeer {
     int tail_rows = 0;                                        // rows of the short last chunk (filled by the launcher)
 };
 int tiled_pass_peer(const double *phi_in, double *phi_out, const double *D, int W, int H, int row_first, int rows, int grow0,
-                    int nsweeps, unsigned long long *slots, const WavePeer &peer, cudaStream_t stream);
+                    int nsweeps, unsigned long long *slots, const WavePeer &peer, int sm_count, int sm_reserve,
+                    cudaStream_t stream);
 
 }  // namespace pcd

@@ -148,7 +148,7 @@ static int run_tiled(pcd_solver *s, const double *D, double *phi, int max_it, do
         PCD_CUDA(cudaEventRecord(s->evk0, s->stream));
         for (int j = 0; j < k;) {
             const int ns = k - j < TS ? k - j : TS;
-            PCD_TRY(tiled_pass(cur, alt, D, W, H, 0, H, 0, ns, s->sweep_max + j, s->stream));
+            PCD_TRY(tiled_pass(cur, alt, D, W, H, 0, H, 0, ns, s->sweep_max + j, s->sm_count, 0, s->stream));
             info->launches++;
             double *t = cur; cur = alt; alt = t;
             j += ns;

@@ -17,6 +17,7 @@ constexpr size_t PCD_SLAB_CTL_BYTES = 256;
 
 struct pcd_slab {
     int W = 0, H = 0, row0 = 0, rows = 0, device = 0, GH = 0;
+    int sm_count = 0, sm_reserve = 0;   // SMs of this slab's device / SMs its passes leave free for an overlapped exchange
     cudaStream_t stream = nullptr;   // caller's stream (e.g. torch's current stream), never owned
     double *phi[2] = {nullptr, nullptr};  // (rows + 2*GH) x W each; phi[cur] holds the field
     double *D = nullptr;
@@ -88,6 +89,9 @@ sor_slab_colour_kernel(double *__restrict__ phi, const double *__restrict__ D, c
     }
 }
 
+// the slab's error word as a double next to the per-sweep maxima, so it rides in the same all-reduce (MAX)
+__global__ void slab_error_to_kernel(const unsigned *err, double *dst) { *dst = *err ? 1.0 : 0.0; }
+
 }  // namespace pcd
 
 using namespace pcd;
@@ -96,7 +100,11 @@ extern "C" {
 
 int pcd_slab_ghost_rows(void) { return 2 * tiled_sweeps_per_pass() + 1; }
 int pcd_slab_sweeps_per_pass(void) { return tiled_sweeps_per_pass(); }
-void pcd_slab_set_sm_reserve(int n) { tiled_set_sm_reserve(n); }
+int pcd_slab_set_sm_reserve(pcd_slab *s, int n) {
+    if (!s) { set_error("null slab"); return PCD_ERR_INVALID; }
+    s->sm_reserve = n < 0 ? 0 : n;
+    return PCD_OK;
+}
 
 int pcd_slab_create(int width, int height, int row0, int rows, int device, void *cuda_stream, pcd_slab **out) {
     if (!out) { set_error("null argument"); return PCD_ERR_INVALID; }
@@ -109,6 +117,7 @@ int pcd_slab_create(int width, int height, int row0, int rows, int device, void 
     pcd_slab *s = new pcd_slab();
     s->W = width; s->H = height; s->row0 = row0; s->rows = rows; s->device = device;
     s->GH = pcd_slab_ghost_rows();
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     s->stream = (cudaStream_t)cuda_stream;
     s->ring = 4096;
     const size_t n = (size_t)(rows + 2 * s->GH) * width;
@@ -177,6 +186,7 @@ int pcd_slab_upload(pcd_slab *s, const double *D_rows, const double *phi_rows) {
         PCD_CUDA(cudaMemcpyAsync(s->phi[0], phi_rows, bytes, cudaMemcpyHostToDevice, s->stream));
         s->cur = 0;
     }
+    PCD_CUDA(cudaMemsetAsync(s->ctl + 8, 0, sizeof(unsigned), s->stream));   // a new solve starts with a clean error word
     PCD_CUDA(cudaStreamSynchronize(s->stream));
     return PCD_OK;
 }
@@ -194,6 +204,7 @@ int pcd_slab_load_device(pcd_slab *s, const double *D_full, const double *phi_fu
     PCD_CUDA(cudaMemsetAsync(s->phi[0], 0, all, s->stream));
     PCD_CUDA(cudaMemcpyAsync(s->D + off, D_full + (size_t)lo * W, cnt, cudaMemcpyDeviceToDevice, s->stream));
     PCD_CUDA(cudaMemcpyAsync(s->phi[0] + off, phi_full + (size_t)lo * W, cnt, cudaMemcpyDeviceToDevice, s->stream));
+    PCD_CUDA(cudaMemsetAsync(s->ctl + 8, 0, sizeof(unsigned), s->stream));   // a new solve starts with a clean error word
     s->cur = 0;
     PCD_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
     slab_mask_kernel<<<dim3((s->W + 255) / 256, s->rows), 256, 0, s->stream>>>(s->D, s->mask, s->W, s->H, s->row0, s->rows, s->GH,
@@ -242,7 +253,7 @@ int pcd_slab_pass(pcd_slab *s, int nsweeps, int slot) {
     }
     if (s->has_nan) { set_error("pcd_slab_pass: D has NaN holes, use the colour path"); return PCD_ERR_UNSUPPORTED; }
     PCD_TRY(tiled_pass(s->phi[s->cur], s->phi[s->cur ^ 1], s->D, s->W, s->H, s->row0, s->rows, s->row0 - s->GH, nsweeps,
-                       s->sweep_max + slot, s->stream));
+                       s->sweep_max + slot, s->sm_count, s->sm_reserve, s->stream));
     s->cur ^= 1;
     s->launches++;
     return PCD_OK;
@@ -259,7 +270,7 @@ int pcd_slab_pass_part(pcd_slab *s, int nsweeps, int slot, int row_begin, int ro
     }
     if (s->has_nan) { set_error("pcd_slab_pass_part: D has NaN holes, use the colour path"); return PCD_ERR_UNSUPPORTED; }
     PCD_TRY(tiled_pass(s->phi[s->cur], s->phi[s->cur ^ 1], s->D, s->W, s->H, row_begin, row_count, s->row0 - s->GH, nsweeps,
-                       s->sweep_max + slot, cuda_stream ? (cudaStream_t)cuda_stream : s->stream));
+                       s->sweep_max + slot, s->sm_count, s->sm_reserve, cuda_stream ? (cudaStream_t)cuda_stream : s->stream));
     s->launches++;
     return PCD_OK;
 }
@@ -349,7 +360,7 @@ int pcd_slab_peer_run(pcd_slab *s, int nsweeps, int slot) {
             pr.wait_dn = s->ctl + 1; pr.sig_dn = s->peer_ctl[1] + 0;   // I am its upper neighbour
         }
         PCD_TRY(tiled_pass_peer(s->phi[s->cur], s->phi[o], s->D, s->W, s->H, s->row0, s->rows, s->row0 - s->GH, ns,
-                                s->sweep_max + slot + j, pr, s->stream));
+                                s->sweep_max + slot + j, pr, s->sm_count, s->sm_reserve, s->stream));
         s->cur = o;
         s->launches++;
     }
@@ -362,6 +373,13 @@ int pcd_slab_peer_status(pcd_slab *s, int *timed_out) {
     PCD_TRY(select_device(s->device));
     PCD_CUDA(cudaMemcpyAsync(timed_out, s->ctl + 8, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     PCD_CUDA(cudaStreamSynchronize(s->stream));
+    return PCD_OK;
+}
+
+int pcd_slab_peer_error_to(pcd_slab *s, double *dst_dev) {
+    if (!s || !dst_dev) { set_error("null argument"); return PCD_ERR_INVALID; }
+    slab_error_to_kernel<<<1, 1, 0, s->stream>>>(s->ctl + 8, dst_dev);
+    PCD_LAUNCHED();
     return PCD_OK;
 }
 

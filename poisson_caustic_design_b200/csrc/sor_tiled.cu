@@ -325,20 +325,18 @@ __global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __gr
 
 constexpr int TILED_TS = 2;
 int tiled_sweeps_per_pass() { return TILED_TS; }
-static int g_sm_reserve = 0;
-void tiled_set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : n; }
 
 template <int TS, bool PEER>
-static int launch_wave(const WaveParams &prm, int sm_count, cudaStream_t stream) {
+static int launch_wave(const WaveParams &prm, int sm_count, int sm_reserve, cudaStream_t stream) {
     using Cfg = WaveCfg<TS>;
     const size_t smem = (size_t)2 * Cfg::R * 2 * Cfg::PITCH * sizeof(double);
-    {   // the opt-in is per device: remember which devices have it
-        static unsigned long long done_mask = 0ull;
+    {   // the opt-in is per device: remember which devices have it (contexts on several threads may race here: atomic)
+        static std::atomic<unsigned long long> done_mask{0ull};
         int dev = 0;
         PCD_CUDA(cudaGetDevice(&dev));
-        if (dev >= 64 || !((done_mask >> dev) & 1ull)) {
+        if (dev >= 64 || !((done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
             PCD_CUDA(cudaFuncSetAttribute(sor_wave_kernel<TS, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (dev < 64) done_mask |= 1ull << dev;
+            if (dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
         }
     }
     WaveParams p = prm;
@@ -347,7 +345,7 @@ static int launch_wave(const WaveParams &prm, int sm_count, cudaStream_t stream)
     // rows 19.8 us/sweep, 32 chunks of 64 rows 28.6): the row step is latency-bound, so the shortest chunks that
     // still fit one wave win even though the 2*NP warm-up rows are then a larger share of the work
     // (multi-GPU runs keep a few SMs free so that the NCCL kernels of the overlapped ghost-row exchange can run)
-    const int avail = (sm_count - g_sm_reserve >= 8) ? sm_count - g_sm_reserve : sm_count;
+    const int avail = (sm_count - sm_reserve >= 8) ? sm_count - sm_reserve : sm_count;
     int chunks = (WAVE_CTAS * avail) / strips;
     int min_rows = 4 * Cfg::NP;  // a step costs the same latency whatever the chunk length: fill the wave first
     static const int dbg_chunks = getenv("PCD_WAVE_CHUNKS") ? atoi(getenv("PCD_WAVE_CHUNKS")) : 0;  // tuning knob
@@ -372,36 +370,25 @@ static int launch_wave(const WaveParams &prm, int sm_count, cudaStream_t stream)
 // phi_in.  Arrays have local row 0 = global row grow0 and must hold rows row_first-2*nsweeps-1 ..
 // row_first+rows+2*nsweeps-1 (clipped to the grid) of the current field.
 int tiled_pass(const double *phi_in, double *phi_out, const double *D, int W, int H, int row_first, int rows, int grow0,
-               int nsweeps, unsigned long long *slots, cudaStream_t stream) {
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        PCD_CUDA(cudaGetDevice(&dev));
-        PCD_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+               int nsweeps, unsigned long long *slots, int sm_count, int sm_reserve, cudaStream_t stream) {
     WaveParams prm;
     prm.phi_in = phi_in; prm.phi_out = phi_out; prm.D = D; prm.W = W; prm.H = H;
     prm.row_first = row_first; prm.rows = rows; prm.grow0 = grow0; prm.nchunks = 1;
     prm.w = make_w(W); prm.slots = slots;
-    if (nsweeps >= 2) return launch_wave<2, false>(prm, sm_count, stream);
-    return launch_wave<1, false>(prm, sm_count, stream);
+    if (nsweeps >= 2) return launch_wave<2, false>(prm, sm_count, sm_reserve, stream);
+    return launch_wave<1, false>(prm, sm_count, sm_reserve, stream);
 }
 
 // The same pass over a whole slab with the ghost-row exchange fused in (see WavePeer).
 int tiled_pass_peer(const double *phi_in, double *phi_out, const double *D, int W, int H, int row_first, int rows, int grow0,
-                    int nsweeps, unsigned long long *slots, const WavePeer &peer, cudaStream_t stream) {
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        PCD_CUDA(cudaGetDevice(&dev));
-        PCD_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+                    int nsweeps, unsigned long long *slots, const WavePeer &peer, int sm_count, int sm_reserve,
+                    cudaStream_t stream) {
     WaveParams prm;
     prm.phi_in = phi_in; prm.phi_out = phi_out; prm.D = D; prm.W = W; prm.H = H;
     prm.row_first = row_first; prm.rows = rows; prm.grow0 = grow0; prm.nchunks = 1;
     prm.w = make_w(W); prm.slots = slots; prm.peer = peer;
-    if (nsweeps >= 2) return launch_wave<2, true>(prm, sm_count, stream);
-    return launch_wave<1, true>(prm, sm_count, stream);
+    if (nsweeps >= 2) return launch_wave<2, true>(prm, sm_count, sm_reserve, stream);
+    return launch_wave<1, true>(prm, sm_count, sm_reserve, stream);
 }
 
 }  // namespace pcd

@@ -131,6 +131,14 @@ class CudaSlabEngine:
         _check(lib().pcd_slab_peer_status(self._h, C.byref(t)))
         return bool(t.value)
 
+    def peer_error_into(self, slot):
+        """The slab's error word (1.0 = a pass ran into its time limit waiting for a neighbour) into the one-element
+        device tensor `slot`, asynchronously on the slab's stream."""
+        _check(lib().pcd_slab_peer_error_to(self._h, C.c_void_p(slot.data_ptr())))
+
+    def set_sm_reserve(self, n: int):
+        _check(lib().pcd_slab_set_sm_reserve(self._h, n))
+
     def load_device(self, D_dev: int, phi_dev: int):
         """D and phi (ghost rows included) from full W x H device arrays on this GPU."""
         _check(lib().pcd_slab_load_device(self._h, C.c_void_p(D_dev), C.c_void_p(phi_dev)))
@@ -240,66 +248,77 @@ def solve(engine, dist, rank: int, world: int, max_iterations: int, tol: float, 
         side = torch.cuda.Stream()
         ev_bands, ev_xchg = torch.cuda.Event(), torch.cuda.Event()
         edge_bands, interior = engine.bands()
-        lib().pcd_slab_set_sm_reserve(8)   # room for the NCCL send/recv kernels next to the interior pass
+        engine.set_sm_reserve(8)   # room for the NCCL send/recv kernels next to the interior pass (this slab only)
     done, conv, last = 0, 0, 0.0
-    while done < max_iterations and not conv:
-        k = min(check_every, max_iterations - done)
-        engine.clear_max(k)
-        if wave and overlap:
-            j = 0
-            while j < k:
-                ns = min(TS, k - j)
-                for (rb, rc) in edge_bands:
-                    engine.pass_part(ns, j, rb, rc)
-                ev_bands.record(main)
-                engine.pass_part(ns, j, interior[0], interior[1])
-                engine.flip()
-                with torch.cuda.stream(side):
-                    side.wait_event(ev_bands)
-                    _exchange(engine, dist, rank, world, engine.GH)   # on the buffer the pass just filled
-                    ev_xchg.record(side)
-                main.wait_event(ev_xchg)
-                j += ns
-        elif wave:
-            j = 0
-            while j < k:
-                ns = min(TS, k - j)
-                engine.pass_(ns, j)
-                if world > 1:
-                    _exchange(engine, dist, rank, world, engine.GH)
-                j += ns
-        else:
-            for j in range(k):
-                for colour in (0, 1):
-                    engine.sweep_colour(colour, j)
+    try:
+        while done < max_iterations and not conv:
+            k = min(check_every, max_iterations - done)
+            engine.clear_max(k)
+            if wave and overlap:
+                j = 0
+                while j < k:
+                    ns = min(TS, k - j)
+                    for (rb, rc) in edge_bands:
+                        engine.pass_part(ns, j, rb, rc)
+                    ev_bands.record(main)
+                    engine.pass_part(ns, j, interior[0], interior[1])
+                    engine.flip()
+                    with torch.cuda.stream(side):
+                        side.wait_event(ev_bands)
+                        _exchange(engine, dist, rank, world, engine.GH)   # on the buffer the pass just filled
+                        ev_xchg.record(side)
+                    main.wait_event(ev_xchg)
+                    j += ns
+            elif wave:
+                j = 0
+                while j < k:
+                    ns = min(TS, k - j)
+                    engine.pass_(ns, j)
                     if world > 1:
-                        _exchange(engine, dist, rank, world, 1)
-        m = engine.max_tensor(k).clone()
-        if world > 1:
-            dist.all_reduce(m, op=dist.ReduceOp.MAX)
-        m_host = m.cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
-        conv, last = _decide(m_host, tol, done)
-        done += k
-    if overlap:
-        lib().pcd_slab_set_sm_reserve(0)   # process-wide setting: give the SMs back to later solves
+                        _exchange(engine, dist, rank, world, engine.GH)
+                    j += ns
+            else:
+                for j in range(k):
+                    for colour in (0, 1):
+                        engine.sweep_colour(colour, j)
+                        if world > 1:
+                            _exchange(engine, dist, rank, world, 1)
+            m = engine.max_tensor(k).clone()
+            if world > 1:
+                dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            m_host = m.cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
+            conv, last = _decide(m_host, tol, done)
+            done += k
+    finally:
+        if overlap:
+            engine.set_sm_reserve(0)   # also when the loop raised: later solves on this slab get every SM back
     return {"sweeps": done, "converged_at": conv, "last_max_update": last, "mode": "wavefront" if wave else "colour"}
 
 
 def _solve_peer(engine, dist, world: int, max_iterations: int, tol: float, check_every: int):
     """Fused path: a block of check_every sweeps is nothing but back-to-back pass kernels (the ghost rows travel
     inside them); the only collective is the all-reduce of the per-sweep maxima at the end of the block."""
-    check_every = max(1, min(check_every, 4096))
+    import torch
+    check_every = max(1, min(check_every, 4095))
     done, conv, last = 0, 0, 0.0
     while done < max_iterations and not conv:
         k = min(check_every, max_iterations - done)
         engine.clear_max(k)
         engine.peer_run(k, 0)
-        m = engine.max_tensor(k).clone()
+        # the block's maxima plus, in the last slot, this rank's error word (a pass that waited ~3 s in vain for a
+        # neighbour): one all-reduce (MAX) tells EVERY rank about a stalled neighbour in the same block, so all ranks
+        # stop together instead of launching further passes on invalid ghost rows or blocking in a later collective
+        src = engine.max_tensor(k)
+        m = torch.empty(k + 1, dtype=src.dtype, device=src.device)
+        m[:k].copy_(src)
+        engine.peer_error_into(m[k:])
         dist.all_reduce(m, op=dist.ReduceOp.MAX)
-        conv, last = _decide(m.cpu().numpy(), tol, done)
+        m_host = m.cpu().numpy()
+        if m_host[k] != 0.0:
+            raise RuntimeError("slab solve: a pass gave up waiting for a neighbouring rank's ghost rows "
+                               f"(reported by at least one rank in sweeps {done + 1}..{done + k}; every rank stops here)")
+        conv, last = _decide(m_host[:k], tol, done)
         done += k
-    if engine.peer_timed_out():
-        raise RuntimeError("slab solve: a pass gave up waiting for a neighbouring rank's ghost rows")
     return {"sweeps": done, "converged_at": conv, "last_max_update": last, "mode": "peer"}
 
 
@@ -421,12 +440,14 @@ class SlabSolveHook:
         try:
             eng = self.engine
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            eng.load_device(D_dev, phi_dev)
+            eng.load_device(D_dev, phi_dev)    # also clears the slab's error word: a failed solve does not poison the next
             e0.record()
             r = solve(eng, self.dist, self.rank, self.world, max_it, tol, self.check_every, self.mode)
             e1.record()
             eng.store_device(phi_dev)
             if self.world > 1:   # every rank continues with the whole field
+                # (a stalled neighbour makes solve() raise on EVERY rank in the same block -- the error word rides in
+                # the all-reduce of the maxima -- so no rank reaches these broadcasts alone)
                 phi = torch.as_tensor(_DevView(phi_dev, (H, W), "<f8"), device=torch.device("cuda", self.device))
                 for src in range(self.world):
                     r0, n = partition(H, self.world, src)

@@ -9,6 +9,8 @@ committed, this script is their provenance.
     python tests/golden/make_golden.py full c1|c2|c3      # end-to-end runs (main.cpp:216-262), threads=1
     python tests/golden/make_golden.py stages             # per-stage dumps on small meshes
     python tests/golden/make_golden.py solver             # poisson_solver known-answer cases
+    python tests/golden/make_golden.py c4                 # BASELINE.json configs[3] (the bench workload): 2 iterations
+    python tests/golden/make_golden.py c1height           # C1's first height problem: divergence + the reference's h
 """
 from __future__ import annotations
 
@@ -223,6 +225,68 @@ def cmd_solver():
     print("solver ok")
 
 
+def cmd_c4(n_iters: int = 2):
+    """BASELINE.json configs[3] -- the workload bench.py's metric is quoted on: synthetic 1024x1024 density
+    (synth.synth_density(1024, 1024, 1024)), mesh 256x256, width 1, thickness 0.2.  First `n_iters` transport
+    iterations of the reference, threads=1 (deterministic); ~2 min per iteration."""
+    from poisson_caustic_design_b200 import synth
+    ref = O.RefLib()
+    W = H = 1024
+    img = synth.synth_density(W, H, 1024)
+    st = synth.Setup(256, W, H, mesh_width=1.0, focal_l=1.5, thickness=0.2)
+    s = O.Setup(st.mesh_nx, st.mesh_ny, st.res_x, st.res_y, st.width, st.height, st.focal_l, st.thickness)
+    d = ref.design(s, threads=1)
+    t0 = time.time()
+    d.initialize_solvers(img)
+    ta = d.get("target_areas")
+    out = {"params": np.array([s.mesh_nx, s.mesh_ny, s.res_x, s.res_y, s.width, s.height, s.focal_l, s.thickness]),
+           "image_md5": np.frombuffer(__import__("hashlib").md5(img.tobytes()).hexdigest().encode(), dtype=np.uint8),
+           "target_areas_sub2": np.ascontiguousarray(ta.reshape(s.mesh_ny, s.mesh_nx)[::2, ::2]).ravel(),
+           "target_areas_sum": np.array([ta.sum()]), "vertex_sub": np.array([2])}
+    steps = []
+    for it in range(n_iters):
+        steps.append(d.transport_iteration())
+        print(f"[c4] iter {it} step {steps[-1]:.9f} ({time.time() - t0:.0f}s)", flush=True)
+        for f in ("target_x", "target_y", "errors"):
+            out[f"it{it}_{f}_sub2"] = np.ascontiguousarray(d.get(f).reshape(s.mesh_ny, s.mesh_nx)[::2, ::2]).ravel()
+        phi = d.get("phi")
+        gx, gy = ref.gradient(phi)
+        out[f"it{it}_phi_sub8"] = np.ascontiguousarray((phi - phi.mean())[::8, ::8])
+        out[f"it{it}_grad_absmax"] = np.array([max(np.abs(gx).max(), np.abs(gy).max())])
+        out[f"it{it}_gx_sub8"] = np.ascontiguousarray(gx[::8, ::8])
+        out[f"it{it}_gy_sub8"] = np.ascontiguousarray(gy[::8, ::8])
+        ras = d.get("raster")
+        out[f"it{it}_raster_sub8"] = np.ascontiguousarray(ras[::8, ::8])
+    out["steps"] = np.array(steps)
+    out["source_x_sub2"] = np.ascontiguousarray(d.get("source_x").reshape(s.mesh_ny, s.mesh_nx)[::2, ::2]).ravel()
+    out["source_y_sub2"] = np.ascontiguousarray(d.get("source_y").reshape(s.mesh_ny, s.mesh_nx)[::2, ::2]).ravel()
+    out["wall_s"] = np.array([time.time() - t0])
+    d.close()
+    np.savez_compressed(os.path.join(GOLD, "c4_first_iterations.npz"), **out)
+    print(f"[c4] done in {time.time() - t0:.0f}s, steps {steps}")
+
+
+def cmd_c1height():
+    """The right-hand side and the reference's answer of C1's FIRST height solve (src/caustic_design.cpp:311, tol
+    1e-8, 2066 lexicographic sweeps): input of the truncation-error evidence test."""
+    cfg = FULL["c1"]
+    ref = O.RefLib()
+    gray = gray_of(load_rgb(cfg["image"]))
+    s, img = O.prepare_image(gray, cfg["res_w"], O.f32(cfg["mesh_width"]), O.f32(cfg["focal_l"]), O.f32(cfg["thickness"]))
+    conv = O.f32(cfg["conv_tres"])
+    d = ref.design(s, threads=1)
+    d.initialize_solvers(img)
+    n = 0
+    for itr in range(50):
+        n += 1
+        if d.transport_iteration() < conv:
+            break
+    d.height_iteration(0)
+    np.savez_compressed(os.path.join(GOLD, "c1_height_problem.npz"), divergence=d.get("divergence"), h=d.get("h"),
+                        transport_iterations=np.array([n]))
+    print("c1height ok", n)
+
+
 if __name__ == "__main__":
     cmd = sys.argv[1]
     if cmd == "images":
@@ -233,6 +297,10 @@ if __name__ == "__main__":
         cmd_stages()
     elif cmd == "solver":
         cmd_solver()
+    elif cmd == "c4":
+        cmd_c4()
+    elif cmd == "c1height":
+        cmd_c1height()
     elif cmd == "trim":
         cmd_trim()
     else:

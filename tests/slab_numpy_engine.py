@@ -90,9 +90,10 @@ class NumpyPeerEngine(NumpySlabEngine):
     gloo send/recv issued from inside the engine, so slab.solve's peer path (handle all-gather, agreement, block
     structure, status check) runs on CPU."""
 
-    def __init__(self, W, H, row0, rows, dist, rank, world, fail_connect=False):
+    def __init__(self, W, H, row0, rows, dist, rank, world, fail_connect=False, stall_after_runs=0):
         super().__init__(W, H, row0, rows)
         self.dist, self.rank, self.world, self.fail_connect = dist, rank, world, fail_connect
+        self.stall_after_runs = stall_after_runs   # > 0: this rank's passes report a stalled neighbour from that run on
         self.neighbours = {}
         self.runs = 0
 
@@ -116,4 +117,7 @@ class NumpyPeerEngine(NumpySlabEngine):
             slab._exchange(self, self.dist, self.rank, self.world, self.GH)
 
     def peer_timed_out(self):
-        return False
+        return bool(self.stall_after_runs and self.runs >= self.stall_after_runs)
+
+    def peer_error_into(self, slot):
+        slot[0] = 1.0 if self.peer_timed_out() else 0.0

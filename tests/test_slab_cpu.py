@@ -146,3 +146,44 @@ def test_gloo_peer_mode_host_logic(port, failing_rank, tmp_path):
         assert np.array_equal(i, infos[0])
     want, n, conv, last = port.poisson_rb(D, phi0, 21, 0.0)
     assert int(infos[0][0]) == 21 and np.array_equal(phi, want) and infos[0][2] == last
+
+
+def _stall_worker(rank, world, port, D, phi0, out_dir, stalled_rank):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from poisson_caustic_design_b200 import slab
+    from slab_numpy_engine import NumpyPeerEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    H, W = D.shape
+    row0, rows = slab.partition(H, world, rank)
+    eng = NumpyPeerEngine(W, H, row0, rows, dist, rank, world, stall_after_runs=2 if rank == stalled_rank else 0)
+    eng.upload(slab.with_ghosts(D, row0, rows, eng.GH), slab.with_ghosts(phi0, row0, rows, eng.GH))
+    raised = 0
+    try:
+        slab.solve(eng, dist, rank, world, 100, 0.0, 8)
+    except RuntimeError as e:
+        raised = 1
+        assert "gave up waiting" in str(e)
+    # every rank left the solve after the SAME block (the one in which the stalled rank reported), so this
+    # collective -- the hook's broadcasts in the product -- lines up again on all ranks
+    t = torch.tensor([eng.runs], dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    np.save(os.path.join(out_dir, f"stall_{rank}.npy"), np.array([raised, eng.runs, int(t.item())]))
+    dist.destroy_process_group()
+
+
+def test_gloo_peer_mode_stalled_neighbour_stops_every_rank_together(tmp_path):
+    """ADVICE r01 (slab.py timeout flag): the error word of a rank whose pass waited in vain rides in the block's
+    all-reduce, so all ranks raise in the same block instead of one rank raising while the others block in a
+    later collective."""
+    world = 3
+    rng = np.random.RandomState(5)
+    H, W = 47, 22
+    D = rng.standard_normal((H, W))
+    D -= D.mean()
+    mp.spawn(_stall_worker, args=(world, 29691, D, np.zeros_like(D), str(tmp_path), 1), nprocs=world, join=True)
+    res = [np.load(tmp_path / f"stall_{r}.npy") for r in range(world)]
+    for r in res:
+        assert r[0] == 1 and r[1] == 2 and r[2] == 2      # all raised, all after the second block
