@@ -67,7 +67,11 @@ typedef enum pcd_solver_path {
     PCD_SOLVER_AUTO = 0,       /* resident when the grid fits on chip, tiled otherwise */
     PCD_SOLVER_STREAMING = 1,  /* one launch per colour, phi/D streamed from HBM/L2 (also the NaN-hole path) */
     PCD_SOLVER_RESIDENT = 2,   /* one persistent cooperative kernel, phi/D live in registers/shared memory */
-    PCD_SOLVER_TILED = 3       /* temporal blocking: several sweeps per pass over shared-memory tiles, ping-pong fields */
+    PCD_SOLVER_TILED = 3,      /* temporal blocking: several sweeps per pass over shared-memory tiles, ping-pong fields */
+    PCD_SOLVER_DCT = 4         /* OPT-IN direct backend: the converged field of the same discrete operator by
+                                  a DCT-II diagonalisation (four fp64 GEMMs); ignores max_iterations / tol / warm start, so it
+                                  is not the parity path (the reference stops at max|delta| < tol); never chosen by AUTO;
+                                  D with NaN holes falls back to the masked sweeps */
 } pcd_solver_path;
 
 typedef struct pcd_config {
@@ -215,6 +219,23 @@ int pcd_slab_peer_status(pcd_slab *s, int *timed_out);
  * and every rank learns about a stalled neighbour in the same block.  The word is cleared by pcd_slab_upload /
  * pcd_slab_load_device (a new solve starts clean). */
 int pcd_slab_peer_error_to(pcd_slab *s, double *dst_dev);
+
+/* ---- one Poisson problem on several GPUs of ONE process (the C++ host's --gpus N; torch-free) ------------------
+ * The grid is cut into one row slab per entry of `devices` (the same device may appear several times: G slabs on one
+ * GPU, the emulation used by single-GPU tests); neighbouring slabs exchange ghost rows inside the persistent pass
+ * kernel through peer access.  pcd_multi_solve has the contract of pcd_solver_run with DEVICE arrays on devices[0];
+ * pcd_multi_attach installs it as the Poisson solver of a context created on devices[0] (pcd_set_solve_hook), so the
+ * reference call it stands behind is poisson_solver as issued at src/caustic_design.cpp:222,311.  Bit-identical to
+ * the single-GPU large-grid solver.  NaN holes, or slabs thinner than 2 * pcd_slab_ghost_rows() rows, run on
+ * devices[0] alone.  Destroy (or detach) the solver before the context it is attached to. */
+typedef struct pcd_multi pcd_multi;
+int pcd_multi_create(int width, int height, const int *devices, int n_devices, pcd_multi **out);
+void pcd_multi_destroy(pcd_multi *m);
+int pcd_multi_device_count(const pcd_multi *m);
+int pcd_multi_set_check_every(pcd_multi *m, int sweeps);   /* sweeps between convergence checks (default 64) */
+int pcd_multi_solve(pcd_multi *m, const double *D_dev, double *phi_dev, int max_iterations, double convergence_threshold,
+                    pcd_solve_info *info /* may be NULL */);
+int pcd_multi_attach(pcd_multi *m, pcd_ctx *ctx /* NULL detaches */);
 
 #ifdef __cplusplus
 }

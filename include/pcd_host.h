@@ -48,6 +48,7 @@ typedef struct pcd_cli_options {   /* defaults: main.cpp:175-183 */
     int device;
     int solver_path;
     int quiet;
+    int gpus;          /* --gpus N: Poisson solves as row slabs on devices device .. device+N-1 (default 1) */
 } pcd_cli_options;
 /* returns 0 ok, 1 parse error (message in pcd_host_last_error) */
 int pcd_host_parse_cli(int argc, const char *const *argv, pcd_cli_options *out);

@@ -119,6 +119,12 @@ ABI = [
     ("pcd_slab_peer_run", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("pcd_slab_peer_status", C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     ("pcd_slab_peer_error_to", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("pcd_multi_create", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    ("pcd_multi_destroy", None, [C.c_void_p]),
+    ("pcd_multi_device_count", C.c_int, [C.c_void_p]),
+    ("pcd_multi_set_check_every", C.c_int, [C.c_void_p, C.c_int]),
+    ("pcd_multi_solve", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.POINTER(pcd_solve_info)]),
+    ("pcd_multi_attach", C.c_int, [C.c_void_p, C.c_void_p]),
 ]
 
 
@@ -195,6 +201,9 @@ class Solver:
     def upload(self, D=None, phi=None):
         d = np.ascontiguousarray(D, dtype=np.float64) if D is not None else None
         p = np.ascontiguousarray(phi, dtype=np.float64) if phi is not None else None
+        for name, a in (("D", d), ("phi", p)):
+            if a is not None and a.size != self.W * self.H:   # the C ABI takes plain pointers: sizes are checked here
+                raise PcdError(PCD_ERR_INVALID, f"{name} has {a.size} elements, the solver's grid {self.W}x{self.H}")
         _check(lib().pcd_solver_upload(self._h, _p(d) if d is not None else None, _p(p) if p is not None else None))
 
     def download(self) -> np.ndarray:
@@ -216,6 +225,35 @@ class Solver:
         info = pcd_solve_info()
         _check(lib().pcd_solver_run(self._h, int(max_iterations), float(tol), C.byref(info)))
         return info.as_dict()
+
+
+class MultiGpuSolver:
+    """One Poisson problem as row slabs on several GPUs of this process (include/pcd.h: pcd_multi_*)."""
+
+    def __init__(self, width: int, height: int, devices):
+        self.W, self.H = width, height
+        devs = (C.c_int * len(devices))(*devices)
+        self._h = C.c_void_p()
+        _check(lib().pcd_multi_create(width, height, devs, len(devices), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().pcd_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def set_check_every(self, sweeps: int):
+        _check(lib().pcd_multi_set_check_every(self._h, sweeps))
+
+    def solve(self, D_dev: int, phi_dev: int, max_iterations: int, tol: float) -> dict:
+        """D_dev / phi_dev: raw device pointers (devices[0]) of W x H float64 arrays; phi in/out."""
+        info = pcd_solve_info()
+        _check(lib().pcd_multi_solve(self._h, C.c_void_p(D_dev), C.c_void_p(phi_dev), int(max_iterations), float(tol), C.byref(info)))
+        return info.as_dict()
+
+    def attach(self, design: "CausticDesign | None"):
+        _check(lib().pcd_multi_attach(self._h, design._h if design is not None else None))
 
 
 class CausticDesign:

@@ -1,0 +1,221 @@
+// One Poisson problem on several GPUs of THIS process (SURVEY 8e from the C++ host: `caustic_design --gpus N`), no
+// torch, no NCCL: the grid is cut into row slabs (sor_slab.cu), one per entry of `devices`; neighbouring slabs are
+// attached to each other through peer access and exchange their ghost rows INSIDE the persistent pass kernel (plain
+// stores into the neighbour's HBM over NVLink + per-strip sequence flags, sor_tiled.cu).  The host thread only
+// launches one kernel per slab and block of `check_every` sweeps and reduces the per-sweep maxima of the slabs (exact:
+// max of maxima), so the result is bit-identical to the single-GPU large-grid solver, which tests the stopping rule on
+// the same schedule.  The same device may appear several times in `devices` (G slabs on one GPU: the emulation the
+// single-GPU tests use); its slabs then share a stream and are advanced pass by pass.
+//
+// Replaces nothing in the reference (its only parallelism is the thread tiling of src/solver.cpp:73-83); it sits
+// behind the same call, poisson_solver(D, phi, ...) as issued at src/caustic_design.cpp:222,311, through
+// pcd_set_solve_hook.
+#include <cstring>
+#include <vector>
+
+#include "sor_common.cuh"
+
+struct pcd_multi {
+    int W = 0, H = 0, n = 0;
+    int check_every = 64;
+    std::vector<int> dev;
+    std::vector<pcd_slab *> slabs;
+    std::vector<cudaStream_t> streams;          // one per slab; slabs on the same device share one
+    std::vector<bool> owns_stream;
+    std::vector<unsigned long long *> h_max;    // pinned, 4096 per slab
+    std::vector<unsigned long long *> d_max;    // the slabs' per-sweep maxima (device)
+    bool shared_devices = false;
+    bool peers = false;                          // every slab thick enough for the fused exchange
+    pcd_solver fallback;                         // single-GPU solver on devices[0]: NaN holes, slabs too thin
+    bool fallback_ready = false;
+    pcd_ctx *attached = nullptr;
+};
+
+using namespace pcd;
+
+static int multi_hook(void *user, const double *D_dev, double *phi_dev, int width, int height, int max_iterations, double tol,
+                      pcd_solve_info *info) {
+    pcd_multi *m = static_cast<pcd_multi *>(user);
+    if (width != m->W || height != m->H) { set_error("pcd_multi: attached to a %dx%d context, built for %dx%d", width, height, m->W, m->H); return PCD_ERR_INVALID; }
+    return pcd_multi_solve(m, D_dev, phi_dev, max_iterations, tol, info);
+}
+
+extern "C" {
+
+int pcd_multi_create(int width, int height, const int *devices, int n_devices, pcd_multi **out) {
+    if (!out || !devices || n_devices < 1 || width < 1 || height < n_devices) {
+        set_error("pcd_multi_create: bad arguments (%d devices for a %dx%d grid)", n_devices, width, height);
+        return PCD_ERR_INVALID;
+    }
+    *out = nullptr;
+    pcd_multi *m = new pcd_multi();
+    m->W = width; m->H = height; m->n = n_devices;
+    m->dev.assign(devices, devices + n_devices);
+    const int GH = pcd_slab_ghost_rows();
+    int rc = PCD_OK;
+    m->peers = n_devices > 1;
+    for (int g = 0; g < n_devices && rc == PCD_OK; ++g) {
+        rc = select_device(devices[g]);
+        if (rc != PCD_OK) break;
+        cudaStream_t st = nullptr;
+        bool own = true;
+        for (int q = 0; q < g; ++q)
+            if (devices[q] == devices[g]) { st = m->streams[q]; own = false; m->shared_devices = true; break; }
+        if (own && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { set_error("pcd_multi_create: stream creation failed"); rc = PCD_ERR_CUDA; break; }
+        m->streams.push_back(st);
+        m->owns_stream.push_back(own);
+        const int row0 = (int)((long long)g * height / n_devices), row1 = (int)((long long)(g + 1) * height / n_devices);
+        if (row1 - row0 < 2 * GH) m->peers = false;
+        pcd_slab *s = nullptr;
+        rc = pcd_slab_create(width, height, row0, row1 - row0, devices[g], st, &s);
+        if (rc != PCD_OK) break;
+        m->slabs.push_back(s);
+        void *mx = nullptr;
+        pcd_slab_device_ptrs(s, nullptr, nullptr, &mx);
+        m->d_max.push_back(static_cast<unsigned long long *>(mx));
+        unsigned long long *h = nullptr;
+        if (cudaMallocHost(&h, sizeof(unsigned long long) * 4096) != cudaSuccess) { set_error("pcd_multi_create: pinned allocation failed"); rc = PCD_ERR_CUDA; break; }
+        m->h_max.push_back(h);
+    }
+    if (rc == PCD_OK && m->peers)
+        for (int g = 0; g + 1 < n_devices && rc == PCD_OK; ++g) {
+            rc = pcd_slab_peer_connect_local(m->slabs[g], 1, m->slabs[g + 1]);
+            if (rc == PCD_OK) rc = pcd_slab_peer_connect_local(m->slabs[g + 1], 0, m->slabs[g]);
+        }
+    if (rc == PCD_OK) {
+        // the full fields live on devices[0]: let every other device read / write them directly where it can (the
+        // copies fall back to staging through the host where it cannot)
+        for (int g = 1; g < n_devices; ++g) {
+            if (devices[g] == devices[0]) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[g], devices[0]) == cudaSuccess && can) {
+                cudaSetDevice(devices[g]);
+                if (cudaDeviceEnablePeerAccess(devices[0], 0) != cudaSuccess) cudaGetLastError();
+            }
+        }
+        cudaGetLastError();
+    }
+    if (rc != PCD_OK) { pcd_multi_destroy(m); return rc; }
+    *out = m;
+    return PCD_OK;
+}
+
+void pcd_multi_destroy(pcd_multi *m) {
+    if (!m) return;
+    if (m->attached) pcd_set_solve_hook(m->attached, nullptr, nullptr);
+    for (pcd_slab *s : m->slabs) pcd_slab_destroy(s);
+    for (size_t g = 0; g < m->streams.size(); ++g)
+        if (m->owns_stream[g] && m->streams[g]) { cudaSetDevice(m->dev[g]); cudaStreamDestroy(m->streams[g]); }
+    for (unsigned long long *h : m->h_max) cudaFreeHost(h);
+    if (m->fallback_ready) { cudaSetDevice(m->dev[0]); solver_free(&m->fallback); }
+    delete m;
+}
+
+int pcd_multi_set_check_every(pcd_multi *m, int sweeps) {
+    if (!m || sweeps < 1) { set_error("pcd_multi_set_check_every: bad arguments"); return PCD_ERR_INVALID; }
+    const int TS = pcd_slab_sweeps_per_pass();
+    m->check_every = sweeps > 4096 ? 4096 : (sweeps + TS - 1) / TS * TS;
+    return PCD_OK;
+}
+
+int pcd_multi_device_count(const pcd_multi *m) { return m ? m->n : 0; }
+
+// D_dev / phi_dev: width x height arrays on devices[0]; phi in/out (warm start).  Same contract as pcd_solver_run.
+int pcd_multi_solve(pcd_multi *m, const double *D_dev, double *phi_dev, int max_iterations, double tol, pcd_solve_info *info) {
+    if (!m || !D_dev || !phi_dev) { set_error("pcd_multi_solve: null argument"); return PCD_ERR_INVALID; }
+    pcd_solve_info local{};
+    if (!info) info = &local;
+    *info = pcd_solve_info{};
+    info->path = PCD_SOLVER_TILED;
+    if (max_iterations <= 0) return PCD_OK;
+    const int n = m->n;
+    bool nan = false;
+    if (m->peers) {
+        for (int g = 0; g < n; ++g) PCD_TRY(pcd_slab_load_device(m->slabs[g], D_dev, phi_dev));   // waits for its stream
+        for (int g = 0; g < n; ++g) nan = nan || pcd_slab_has_nan(m->slabs[g]) != 0;
+    }
+    if (!m->peers || nan) {
+        // one slab would be thinner than two ghost depths, or D has NaN holes (their neighbour rule needs the masked
+        // per-colour kernels): the whole problem runs on devices[0]
+        PCD_TRY(select_device(m->dev[0]));
+        if (!m->fallback_ready) {
+            PCD_TRY(solver_init(&m->fallback, m->W, m->H, m->dev[0], PCD_SOLVER_AUTO, nullptr));
+            m->fallback_ready = true;
+        }
+        return solver_run(&m->fallback, D_dev, phi_dev, max_iterations, tol, info);
+    }
+    const int TS = pcd_slab_sweeps_per_pass();
+    cudaEvent_t e0, e1;
+    PCD_TRY(select_device(m->dev[0]));
+    PCD_CUDA(cudaEventCreate(&e0));
+    PCD_CUDA(cudaEventCreate(&e1));
+    PCD_CUDA(cudaEventRecord(e0, m->streams[0]));
+    int done = 0, conv = 0;
+    double last = 0.0;
+    while (done < max_iterations && !conv) {
+        const int k = max_iterations - done < m->check_every ? max_iterations - done : m->check_every;
+        for (int g = 0; g < n; ++g) PCD_TRY(pcd_slab_clear_max(m->slabs[g], k));
+        if (m->shared_devices) {     // slabs of one device run one after the other: advance all slabs pass by pass
+            for (int j = 0; j < k; j += TS)
+                for (int g = 0; g < n; ++g) PCD_TRY(pcd_slab_peer_run(m->slabs[g], k - j < TS ? k - j : TS, j));
+        } else {                     // one persistent launch per slab for the whole block
+            for (int g = 0; g < n; ++g) PCD_TRY(pcd_slab_peer_run(m->slabs[g], k, 0));
+        }
+        info->launches += n * ((k + TS - 1) / TS);
+        for (int g = 0; g < n; ++g) {
+            PCD_TRY(select_device(m->dev[g]));
+            PCD_CUDA(cudaMemcpyAsync(m->h_max[g], m->d_max[g], sizeof(unsigned long long) * k, cudaMemcpyDeviceToHost, m->streams[g]));
+        }
+        for (int g = 0; g < n; ++g) {
+            int timed_out = 0;
+            PCD_TRY(pcd_slab_peer_status(m->slabs[g], &timed_out));   // waits for the slab's stream
+            if (timed_out) { set_error("pcd_multi_solve: slab %d gave up waiting for a neighbour's ghost rows", g); return PCD_ERR_CUDA; }
+        }
+        for (int j = 0; j < k; ++j) {
+            double mx = 0.0;
+            for (int g = 0; g < n; ++g) {
+                double v;
+                memcpy(&v, &m->h_max[g][j], sizeof(double));
+                if (v > mx) mx = v;
+            }
+            if (!conv && mx < tol) { conv = done + j + 1; last = mx; }
+            if (!conv && j == k - 1) last = mx;
+        }
+        done += k;
+    }
+    for (int g = 0; g < n; ++g) PCD_TRY(pcd_slab_store_device(m->slabs[g], phi_dev));
+    for (int g = 0; g < n; ++g) {
+        PCD_TRY(select_device(m->dev[g]));
+        PCD_CUDA(cudaStreamSynchronize(m->streams[g]));
+    }
+    PCD_TRY(select_device(m->dev[0]));
+    PCD_CUDA(cudaEventRecord(e1, m->streams[0]));
+    PCD_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    PCD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    info->sweeps = done;
+    info->converged_at = conv;
+    info->last_max_update = last;
+    info->device_ms = info->kernel_ms = ms;
+    return PCD_OK;
+}
+
+// Installs the multi-GPU solver as the Poisson solver of `ctx` (which must live on devices[0] and have the same grid);
+// NULL ctx detaches.  The context's transport and height iterations are unchanged.
+int pcd_multi_attach(pcd_multi *m, pcd_ctx *ctx) {
+    if (!m) { set_error("pcd_multi_attach: null solver"); return PCD_ERR_INVALID; }
+    if (m->attached) { pcd_set_solve_hook(m->attached, nullptr, nullptr); m->attached = nullptr; }
+    if (!ctx) return PCD_OK;
+    if (ctx->cfg.device != m->dev[0] || ctx->cfg.res_x != m->W || ctx->cfg.res_y != m->H) {
+        set_error("pcd_multi_attach: the context (device %d, %dx%d) does not match the solver (device %d, %dx%d)", ctx->cfg.device,
+                  ctx->cfg.res_x, ctx->cfg.res_y, m->dev[0], m->W, m->H);
+        return PCD_ERR_INVALID;
+    }
+    PCD_TRY(pcd_set_solve_hook(ctx, multi_hook, m));
+    m->attached = ctx;
+    return PCD_OK;
+}
+
+}  // extern "C"

@@ -72,6 +72,9 @@ struct pcd_solver {
     void *h_res_state = nullptr;    // pinned mirror
     double *halo = nullptr;         // device: boundary-row exchange buffers
     double *phi_alt = nullptr;      // device: ping-pong partner of phi on the tiled path
+    unsigned *wave_ctl = nullptr;   // device: per-CTA sequence words + error word of the persistent wavefront kernel
+    unsigned wave_seq = 0;          // sequence number of the last pass it executed
+    void *dct_state = nullptr;      // opt-in direct backend (dct_solver.cu): DCT matrices, eigenvalues, temporaries
     int res_ctas = 0, res_threads = 0, res_rows_per_cta = 0, res_n_big = 0;
     int res_pairs = 0;   // CTA-pair (cluster) launch of the resident kernel: 0 undecided, 1 in use, -1 not available
     size_t res_smem = 0;

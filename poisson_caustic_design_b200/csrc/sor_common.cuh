@@ -44,28 +44,39 @@ int resident_plan(pcd_solver *s);   // 1 when the grid fits the on-chip path (fi
 int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double tol, pcd_solve_info *info);
 
 
+// dct_solver.cu: opt-in direct backend (PCD_SOLVER_DCT); D must be free of NaN
+int run_dct(pcd_solver *s, const double *D, double *phi, pcd_solve_info *info);
+void dct_free(pcd_solver *s);
+
 // sor_tiled.cu
 int tiled_sweeps_per_pass();
 // sm_count: SMs of the device the pass runs on; sm_reserve: SMs the pass leaves free (overlapped multi-GPU exchange)
 int tiled_pass(const double *phi_in, double *phi_out, const double *D, int W, int H, int row_first, int rows, int grow0,
                int nsweeps, unsigned long long *slots, int sm_count, int sm_reserve, cudaStream_t stream);
 
-// Ghost-row exchange fused into the wavefront pass (multi-GPU slabs): the CTAs that finish the `gh` owned rows next to
-// a slab edge store them to the neighbour's output field as well (peer memory over NVLink) and the last of them
-// raises the neighbour's flag to `seq`; the CTAs that read ghost rows first wait until their flag reached seq-1.
+// Persistent multi-pass launch of the wavefront kernel with the ghost-row exchange fused in (multi-GPU slabs): the CTAs
+// that finish the `gh` owned rows next to a slab edge store them to the neighbour's output field as well (peer memory
+// over NVLink) and raise THEIR STRIP's flag in the neighbour's memory to the pass's sequence number; the edge CTAs of
+// the next pass wait until the flags of their own and the two adjacent strips have reached the previous sequence number.
+constexpr int WAVE_MAX_CTAS = 1024;   // size of the per-CTA sequence array of a slab
+constexpr int WAVE_MAX_STRIPS = 512;  // size of a per-strip flag array
 struct WavePeer {
-    double *up_out = nullptr, *dn_out = nullptr;  // neighbours' phi_out arrays (local row 0 = global row *_grow0)
+    double *buf[2] = {nullptr, nullptr};                 // this slab's two field buffers (local row 0 = global row grow0)
+    double *up_buf[2] = {nullptr, nullptr};              // the neighbours' buffers, same numbering (nullptr: no neighbour)
+    double *dn_buf[2] = {nullptr, nullptr};
     int up_grow0 = 0, dn_grow0 = 0;
     int gh = 0;
-    const unsigned *wait_up = nullptr, *wait_dn = nullptr;  // local flags, written by the neighbours
-    unsigned *sig_up = nullptr, *sig_dn = nullptr;           // the neighbours' flags
-    unsigned *cnt = nullptr;                                  // local arrival counters [2]
+    int cur = 0;                                          // buffer that holds the field before the first pass
+    int npass = 0;
+    const unsigned *wait_up = nullptr, *wait_dn = nullptr;  // local per-strip flags, written by the neighbours
+    unsigned *sig_up = nullptr, *sig_dn = nullptr;           // the neighbours' per-strip flags this slab raises
+    unsigned *done = nullptr;                                 // local: last published pass per CTA [WAVE_MAX_CTAS]
     int *err = nullptr;                                       // local: set when a wait ran into its time limit
-    unsigned seq = 0;                                         // sequence number of this pass (first pass: 1)
+    unsigned seq0 = 0;                                        // sequence number of the last pass before this launch
     int tail_rows = 0;                                        // rows of the short last chunk (filled by the launcher)
 };
-int tiled_pass_peer(const double *phi_in, double *phi_out, const double *D, int W, int H, int row_first, int rows, int grow0,
-                    int nsweeps, unsigned long long *slots, const WavePeer &peer, int sm_count, int sm_reserve,
-                    cudaStream_t stream);
+int tiled_run_peer(const double *D, int W, int H, int row_first, int rows, int grow0, int sweeps_per_pass,
+                   unsigned long long *slots, const WavePeer &peer, int sm_count, int sm_reserve, cudaStream_t stream);
+int tiled_strips(int W);
 
 }  // namespace pcd

@@ -17,6 +17,9 @@
 //                 messages, so there is no grid-wide barrier and no fence on the critical path; the
 //                 convergence test is a per-sweep atomicMax + arrival counter evaluated with a fixed
 //                 lag by a dedicated control warp.
+#include <cstdlib>
+#include <cstring>
+
 #include "sor_common.cuh"
 
 namespace pcd {
@@ -131,15 +134,23 @@ static int run_streaming(pcd_solver *s, const double *D, double *phi, int max_it
     return PCD_OK;
 }
 
-// Tiled path (sor_tiled.cu): TS sweeps per pass, ping-pong between phi and a second buffer.
+// Tiled path (sor_tiled.cu): TS sweeps per pass, ping-pong between phi and a second buffer.  A block of `chunk` sweeps
+// between two convergence tests is ONE persistent launch (the CTAs synchronise with their neighbours between passes, no
+// kernel boundary); PCD_WAVE_LAUNCH_PER_PASS=1 restores one launch per pass (diagnostics).
 static int run_tiled(pcd_solver *s, const double *D, double *phi, int max_it, double tol, pcd_solve_info *info) {
     const int W = s->W, H = s->H;
     const int TS = tiled_sweeps_per_pass();
     if (!s->phi_alt) PCD_CUDA(cudaMalloc(&s->phi_alt, sizeof(double) * (size_t)W * H));
+    static const bool per_pass = getenv("PCD_WAVE_LAUNCH_PER_PASS") != nullptr;
+    if (!per_pass && !s->wave_ctl) {
+        PCD_CUDA(cudaMalloc(&s->wave_ctl, sizeof(unsigned) * (WAVE_MAX_CTAS + 16)));
+        PCD_CUDA(cudaMemsetAsync(s->wave_ctl, 0, sizeof(unsigned) * (WAVE_MAX_CTAS + 16), s->stream));
+    }
     int chunk = s->check_lag > 0 ? s->check_lag : 64;
     chunk = ((chunk + TS - 1) / TS) * TS;  // whole passes
     if (chunk > 4096) chunk = 4096;
-    double *cur = phi, *alt = s->phi_alt;
+    double *buf[2] = {phi, s->phi_alt};
+    int cur = 0;
     int done = 0, conv = 0;
     double last = 0.0;
     while (done < max_it && !conv) {
@@ -147,15 +158,36 @@ static int run_tiled(pcd_solver *s, const double *D, double *phi, int max_it, do
         PCD_CUDA(cudaMemsetAsync(s->sweep_max, 0, sizeof(unsigned long long) * k, s->stream));
         PCD_CUDA(cudaEventRecord(s->evk0, s->stream));
         for (int j = 0; j < k;) {
-            const int ns = k - j < TS ? k - j : TS;
-            PCD_TRY(tiled_pass(cur, alt, D, W, H, 0, H, 0, ns, s->sweep_max + j, s->sm_count, 0, s->stream));
+            if (per_pass) {
+                const int ns = k - j < TS ? k - j : TS;
+                PCD_TRY(tiled_pass(buf[cur], buf[cur ^ 1], D, W, H, 0, H, 0, ns, s->sweep_max + j, s->sm_count, 0, s->stream));
+                cur ^= 1;
+                j += ns;
+            } else {
+                const int spp = k - j >= TS ? TS : 1;
+                const int npass = k - j >= TS ? (k - j) / TS : k - j;
+                WavePeer pr;
+                pr.buf[0] = buf[0]; pr.buf[1] = buf[1];
+                pr.cur = cur;
+                pr.npass = npass;
+                pr.done = s->wave_ctl;
+                pr.err = reinterpret_cast<int *>(s->wave_ctl + WAVE_MAX_CTAS);
+                pr.seq0 = s->wave_seq;
+                PCD_TRY(tiled_run_peer(D, W, H, 0, H, 0, spp, s->sweep_max + j, pr, s->sm_count, 0, s->stream));
+                s->wave_seq += (unsigned)npass;
+                cur ^= (npass & 1);
+                j += npass * spp;
+            }
             info->launches++;
-            double *t = cur; cur = alt; alt = t;
-            j += ns;
         }
         PCD_CUDA(cudaEventRecord(s->evk1, s->stream));
         PCD_CUDA(cudaMemcpyAsync(s->h_sweep_max, s->sweep_max, sizeof(unsigned long long) * k, cudaMemcpyDeviceToHost, s->stream));
+        if (!per_pass) PCD_CUDA(cudaMemcpyAsync(s->h_flags + 1, s->wave_ctl + WAVE_MAX_CTAS, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         PCD_CUDA(cudaStreamSynchronize(s->stream));
+        if (!per_pass && s->h_flags[1]) {
+            set_error("wavefront K-SOR kernel: a CTA gave up waiting for a neighbouring CTA");
+            return PCD_ERR_CUDA;
+        }
         {
             float kms = 0.f;
             PCD_CUDA(cudaEventElapsedTime(&kms, s->evk0, s->evk1));
@@ -172,7 +204,7 @@ static int run_tiled(pcd_solver *s, const double *D, double *phi, int max_it, do
         }
         done += k;
     }
-    if (cur != phi) PCD_CUDA(cudaMemcpyAsync(phi, cur, sizeof(double) * (size_t)W * H, cudaMemcpyDeviceToDevice, s->stream));
+    if (cur != 0) PCD_CUDA(cudaMemcpyAsync(phi, buf[cur], sizeof(double) * (size_t)W * H, cudaMemcpyDeviceToDevice, s->stream));
     info->sweeps = done;
     info->converged_at = conv;
     info->last_max_update = last;
@@ -211,7 +243,7 @@ int solver_init(pcd_solver *s, int W, int H, int device, int path, cudaStream_t 
     PCD_CUDA(cudaEventCreate(&s->evk0));
     PCD_CUDA(cudaEventCreate(&s->evk1));
     // AUTO: resident when the grid fits on chip, else tiled (temporal blocking); STREAMING = plain colour launches
-    s->path_used = (path == PCD_SOLVER_STREAMING) ? PCD_SOLVER_STREAMING : PCD_SOLVER_TILED;
+    s->path_used = (path == PCD_SOLVER_STREAMING) ? PCD_SOLVER_STREAMING : (path == PCD_SOLVER_DCT ? PCD_SOLVER_DCT : PCD_SOLVER_TILED);
     if (path == PCD_SOLVER_AUTO || path == PCD_SOLVER_RESIDENT) {
         int coop = 0;
         PCD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
@@ -228,9 +260,10 @@ int solver_init(pcd_solver *s, int W, int H, int device, int path, cudaStream_t 
 
 void solver_free(pcd_solver *s) {
     if (!s) return;
+    dct_free(s);
     cudaFree(s->sweep_max); cudaFreeHost(s->h_sweep_max);
     cudaFree(s->mask); cudaFree(s->d_flags); cudaFreeHost(s->h_flags);
-    cudaFree(s->res_state); cudaFreeHost(s->h_res_state); cudaFree(s->halo); cudaFree(s->phi_alt);
+    cudaFree(s->res_state); cudaFreeHost(s->h_res_state); cudaFree(s->halo); cudaFree(s->phi_alt); cudaFree(s->wave_ctl);
     if (s->own_fields) { cudaFree(s->D); cudaFree(s->phi); }
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -267,9 +300,12 @@ int solver_run(pcd_solver *s, const double *D, double *phi, int max_iterations, 
             PCD_LAUNCHED();
             info->launches++;
         }
-        // the tiled path derives neighbour counts from coordinates: NaN holes go through the masked colour kernels
+        // the tiled path derives neighbour counts from coordinates, the direct backend needs the plain operator: NaN
+        // holes go through the masked colour kernels
         if (s->path_used == PCD_SOLVER_TILED && !masked) {
             rc = run_tiled(s, D, phi, max_iterations, tol, info);
+        } else if (s->path_used == PCD_SOLVER_DCT && !masked) {
+            rc = run_dct(s, D, phi, info);
         } else {
             info->path = PCD_SOLVER_STREAMING;
             rc = run_streaming(s, D, phi, max_iterations, tol, masked, info);

@@ -13,7 +13,12 @@
 
 #include "sor_common.cuh"
 
-constexpr size_t PCD_SLAB_CTL_BYTES = 256;
+// Control words behind phi[0] (one CUDA-IPC handle exports the field and them): unsigned ctl[]
+//   [0, 512)     per-strip flags raised by the UPPER neighbour (sequence number of its last pass whose edge rows are here)
+//   [512, 1024)  the same from the LOWER neighbour
+//   [1024]       error word: a pass ran into its time limit waiting for a neighbour
+constexpr int CTL_FROM_UP = 0, CTL_FROM_DN = pcd::WAVE_MAX_STRIPS, CTL_ERR = 2 * pcd::WAVE_MAX_STRIPS;
+constexpr size_t PCD_SLAB_CTL_BYTES = (2 * pcd::WAVE_MAX_STRIPS + 64) * sizeof(unsigned);
 
 struct pcd_slab {
     int W = 0, H = 0, row0 = 0, rows = 0, device = 0, GH = 0;
@@ -29,7 +34,9 @@ struct pcd_slab {
     int ring = 0;
     long long launches = 0;
     // fused peer exchange (pcd_slab_peer_*): control words live behind phi[0] so that one IPC handle covers them
-    unsigned *ctl = nullptr;              // [0],[1]: flags raised by the upper / lower neighbour; [4],[5]: arrival counters; [8]: error
+    unsigned *ctl = nullptr;              // see CTL_* above
+    unsigned *done = nullptr;             // per-CTA sequence words of the persistent pass kernel [WAVE_MAX_CTAS]
+    int passes_per_launch = 0;            // 0 = a whole block of sweeps per launch; 1 when a neighbour shares this device
     double *peer_phi[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [side][buffer], side 0 = up, 1 = down
     unsigned *peer_ctl[2] = {nullptr, nullptr};
     int peer_row0[2] = {0, 0};
@@ -127,6 +134,8 @@ int pcd_slab_create(int width, int height, int row0, int rows, int device, void 
     if (e == cudaSuccess) e = cudaMalloc(&s->mask, n);
     if (e == cudaSuccess) e = cudaMalloc(&s->sweep_max, sizeof(unsigned long long) * s->ring);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_flag, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&s->done, sizeof(unsigned) * WAVE_MAX_CTAS);
+    if (e == cudaSuccess) e = cudaMemset(s->done, 0, sizeof(unsigned) * WAVE_MAX_CTAS);
     if (e == cudaSuccess) e = cudaMemset(s->phi[0], 0, n * sizeof(double) + PCD_SLAB_CTL_BYTES);
     if (e == cudaSuccess) e = cudaMemset(s->phi[1], 0, n * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(s->D, 0, n * sizeof(double));
@@ -136,6 +145,7 @@ int pcd_slab_create(int width, int height, int row0, int rows, int device, void 
     if (e != cudaSuccess) {
         set_error("slab allocation failed: %s", cudaGetErrorString(e));
         cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->D); cudaFree(s->mask); cudaFree(s->sweep_max); cudaFree(s->d_flag);
+        cudaFree(s->done);
         delete s;
         return PCD_ERR_CUDA;
     }
@@ -153,6 +163,7 @@ void pcd_slab_destroy(pcd_slab *s) {
             cudaIpcCloseMemHandle(s->peer_phi[side][1]);
         }
     cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->D); cudaFree(s->mask); cudaFree(s->sweep_max); cudaFree(s->d_flag);
+    cudaFree(s->done);
     delete s;
 }
 
@@ -186,7 +197,7 @@ int pcd_slab_upload(pcd_slab *s, const double *D_rows, const double *phi_rows) {
         PCD_CUDA(cudaMemcpyAsync(s->phi[0], phi_rows, bytes, cudaMemcpyHostToDevice, s->stream));
         s->cur = 0;
     }
-    PCD_CUDA(cudaMemsetAsync(s->ctl + 8, 0, sizeof(unsigned), s->stream));   // a new solve starts with a clean error word
+    PCD_CUDA(cudaMemsetAsync(s->ctl + CTL_ERR, 0, sizeof(unsigned), s->stream));   // a new solve starts with a clean error word
     PCD_CUDA(cudaStreamSynchronize(s->stream));
     return PCD_OK;
 }
@@ -204,7 +215,7 @@ int pcd_slab_load_device(pcd_slab *s, const double *D_full, const double *phi_fu
     PCD_CUDA(cudaMemsetAsync(s->phi[0], 0, all, s->stream));
     PCD_CUDA(cudaMemcpyAsync(s->D + off, D_full + (size_t)lo * W, cnt, cudaMemcpyDeviceToDevice, s->stream));
     PCD_CUDA(cudaMemcpyAsync(s->phi[0] + off, phi_full + (size_t)lo * W, cnt, cudaMemcpyDeviceToDevice, s->stream));
-    PCD_CUDA(cudaMemsetAsync(s->ctl + 8, 0, sizeof(unsigned), s->stream));   // a new solve starts with a clean error word
+    PCD_CUDA(cudaMemsetAsync(s->ctl + CTL_ERR, 0, sizeof(unsigned), s->stream));   // a new solve starts with a clean error word
     s->cur = 0;
     PCD_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
     slab_mask_kernel<<<dim3((s->W + 255) / 256, s->rows), 256, 0, s->stream>>>(s->D, s->mask, s->W, s->H, s->row0, s->rows, s->GH,
@@ -303,6 +314,10 @@ static int peer_attach(pcd_slab *s, int side, double *phi0, double *phi1, int pe
                   peer_row0, peer_row0 + peer_rows, side == 0 ? "upper" : "lower", s->row0, s->row0 + s->rows, 2 * s->GH);
         return PCD_ERR_INVALID;
     }
+    if (tiled_strips(s->W) > WAVE_MAX_STRIPS) {
+        set_error("pcd_slab_peer_connect: a %d-wide grid has more than %d strips", s->W, WAVE_MAX_STRIPS);
+        return PCD_ERR_UNSUPPORTED;
+    }
     s->peer_phi[side][0] = phi0;
     s->peer_phi[side][1] = phi1;
     s->peer_ctl[side] = reinterpret_cast<unsigned *>(phi0 + (size_t)(peer_rows + 2 * s->GH) * s->W);
@@ -331,38 +346,61 @@ int pcd_slab_peer_connect_ipc(pcd_slab *s, int side, const unsigned char *handle
     return rc;
 }
 
-// the neighbour lives in this process on the same device (several slabs per GPU; single-GPU tests of the fused path)
+// The neighbour lives in this process: on the same device (several slabs per GPU: single-GPU tests of the fused path;
+// the slabs' kernels then run one after the other, so every launch is limited to ONE pass) or on another device of
+// this process (the torch-free multi-GPU host, host/multi_gpu.cpp: peer access is enabled here).
 int pcd_slab_peer_connect_local(pcd_slab *s, int side, pcd_slab *peer) {
-    if (!s || !peer || side < 0 || side > 1 || peer->device != s->device || peer->W != s->W) { set_error("bad slab / side / peer"); return PCD_ERR_INVALID; }
+    if (!s || !peer || side < 0 || side > 1 || peer->W != s->W) { set_error("bad slab / side / peer"); return PCD_ERR_INVALID; }
+    if (peer->device != s->device) {
+        PCD_TRY(select_device(s->device));
+        int can = 0;
+        PCD_CUDA(cudaDeviceCanAccessPeer(&can, s->device, peer->device));
+        if (!can) { set_error("device %d cannot access the memory of device %d", s->device, peer->device); return PCD_ERR_UNSUPPORTED; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+        if (e != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess(%d): %s", peer->device, cudaGetErrorString(e)); return PCD_ERR_CUDA; }
+    } else {
+        s->passes_per_launch = 1;
+    }
     return peer_attach(s, side, peer->phi[0], peer->phi[1], peer->row0, peer->rows, false);
 }
 
-// nsweeps sweeps as ceil(nsweeps / TS) fused passes, maxima into slots [slot, slot+nsweeps).  Asynchronous; nothing
-// but kernel launches on the slab's stream.  Every rank must issue the same sequence of peer runs.
+// nsweeps sweeps as ceil(nsweeps / TS) fused passes, maxima into slots [slot, slot+nsweeps).  Asynchronous: ONE persistent
+// launch on the slab's stream for all full passes (plus one for a trailing single sweep).  Every rank must issue the
+// same sequence of peer runs.
 int pcd_slab_peer_run(pcd_slab *s, int nsweeps, int slot) {
     if (!s || slot < 0 || nsweeps < 1 || slot + nsweeps > s->ring) { set_error("bad slab / slot / sweep count"); return PCD_ERR_INVALID; }
     if (s->has_nan) { set_error("pcd_slab_peer_run: D has NaN holes, use the colour path"); return PCD_ERR_UNSUPPORTED; }
+    PCD_TRY(select_device(s->device));
     const int TS = tiled_sweeps_per_pass();
-    for (int j = 0; j < nsweeps; j += TS) {
-        const int ns = nsweeps - j < TS ? nsweeps - j : TS;
-        const int o = s->cur ^ 1;
+    int j = 0;
+    while (j < nsweeps) {
+        const int left = nsweeps - j;
+        const int spp = left >= TS ? TS : 1;                       // sweeps per pass of this launch
+        int npass = left >= TS ? left / TS : left;
+        if (s->passes_per_launch > 0 && npass > s->passes_per_launch) npass = s->passes_per_launch;
         WavePeer pr;
         pr.gh = s->GH;
-        pr.cnt = s->ctl + 4;
-        pr.err = reinterpret_cast<int *>(s->ctl + 8);
-        pr.seq = ++s->seq;
+        pr.buf[0] = s->phi[0]; pr.buf[1] = s->phi[1];
+        pr.cur = s->cur;
+        pr.npass = npass;
+        pr.done = s->done;
+        pr.err = reinterpret_cast<int *>(s->ctl + CTL_ERR);
+        pr.seq0 = s->seq;
         if (s->peer_phi[0][0]) {
-            pr.up_out = s->peer_phi[0][o]; pr.up_grow0 = s->peer_row0[0] - s->GH;
-            pr.wait_up = s->ctl + 0; pr.sig_up = s->peer_ctl[0] + 1;   // I am its lower neighbour
+            pr.up_buf[0] = s->peer_phi[0][0]; pr.up_buf[1] = s->peer_phi[0][1]; pr.up_grow0 = s->peer_row0[0] - s->GH;
+            pr.wait_up = s->ctl + CTL_FROM_UP; pr.sig_up = s->peer_ctl[0] + CTL_FROM_DN;   // I am its lower neighbour
         }
         if (s->peer_phi[1][0]) {
-            pr.dn_out = s->peer_phi[1][o]; pr.dn_grow0 = s->peer_row0[1] - s->GH;
-            pr.wait_dn = s->ctl + 1; pr.sig_dn = s->peer_ctl[1] + 0;   // I am its upper neighbour
+            pr.dn_buf[0] = s->peer_phi[1][0]; pr.dn_buf[1] = s->peer_phi[1][1]; pr.dn_grow0 = s->peer_row0[1] - s->GH;
+            pr.wait_dn = s->ctl + CTL_FROM_DN; pr.sig_dn = s->peer_ctl[1] + CTL_FROM_UP;   // I am its upper neighbour
         }
-        PCD_TRY(tiled_pass_peer(s->phi[s->cur], s->phi[o], s->D, s->W, s->H, s->row0, s->rows, s->row0 - s->GH, ns,
-                                s->sweep_max + slot + j, pr, s->sm_count, s->sm_reserve, s->stream));
-        s->cur = o;
+        PCD_TRY(tiled_run_peer(s->D, s->W, s->H, s->row0, s->rows, s->row0 - s->GH, spp, s->sweep_max + slot + j, pr,
+                               s->sm_count, s->sm_reserve, s->stream));
+        s->seq += (unsigned)npass;
+        s->cur ^= (npass & 1);
         s->launches++;
+        j += npass * spp;
     }
     return PCD_OK;
 }
@@ -371,14 +409,14 @@ int pcd_slab_peer_run(pcd_slab *s, int nsweeps, int slot) {
 int pcd_slab_peer_status(pcd_slab *s, int *timed_out) {
     if (!s || !timed_out) { set_error("null argument"); return PCD_ERR_INVALID; }
     PCD_TRY(select_device(s->device));
-    PCD_CUDA(cudaMemcpyAsync(timed_out, s->ctl + 8, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    PCD_CUDA(cudaMemcpyAsync(timed_out, s->ctl + CTL_ERR, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     PCD_CUDA(cudaStreamSynchronize(s->stream));
     return PCD_OK;
 }
 
 int pcd_slab_peer_error_to(pcd_slab *s, double *dst_dev) {
     if (!s || !dst_dev) { set_error("null argument"); return PCD_ERR_INVALID; }
-    slab_error_to_kernel<<<1, 1, 0, s->stream>>>(s->ctl + 8, dst_dev);
+    slab_error_to_kernel<<<1, 1, 0, s->stream>>>(s->ctl + CTL_ERR, dst_dev);
     PCD_LAUNCHED();
     return PCD_OK;
 }

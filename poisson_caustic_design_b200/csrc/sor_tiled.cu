@@ -16,6 +16,15 @@
 // (staleness advances one row per phase, so owned rows stay exact); per-sweep maxima are taken over owned cells
 // only.  Every owned value equals the global red-black iteration bit for bit.
 //
+// PEER variant (multi-GPU row slabs, and any run of several passes): ONE persistent cooperative launch executes a
+// whole block of passes.  There is no grid-wide barrier between passes: a CTA starts pass q as soon as its (up to)
+// eight neighbouring CTAs have published pass q-1 (a per-CTA sequence word, st.release / ld.acquire at gpu scope) --
+// they are the only CTAs whose output it reads and whose input it overwrites (ping-pong fields) -- and, for the CTAs
+// next to a slab edge, as soon as the neighbouring GPU's edge CTAs of the same and the adjacent strips have raised
+// their per-strip flag for pass q-1 (st.release.sys into this GPU's memory over NVLink).  The edge CTAs store the GH
+// rows next to the slab edge into the neighbour's field as well (plain peer stores) and raise their own strip's flag
+// there as soon as those rows are complete, so the transfer overlaps the rest of the pass.
+//
 // Neighbour rule / update / max: src/solver.cpp:29-56 (no NaN holes on this path: the solver falls back to the
 // masked colour kernels when D contains NaN).
 #include <cuda_pipeline_primitives.h>
@@ -37,14 +46,16 @@ template <int TS>
 struct WaveCfg {
     static constexpr int NP = 2 * TS;                            // colour phases per pass
     static constexpr int R = ((2 * NP + WAVE_PF + 1) + 1) & ~1;  // ring period (rows), even
-    static constexpr int HX = 2 * TS;                            // stale skirt columns on each side of the window
+    static constexpr int HX = 4;                                 // stale skirt columns on each side of the window: 2*TS are needed;
+                                                                 // fixed at the TS = 2 value so that every launch cuts the
+                                                                 // grid into the SAME strips (the per-strip peer flags rely on it)
     static constexpr int LXW = 2 * WAVE_NT;                      // window columns
     static constexpr int CORE = LXW - 2 * HX;                    // columns written by the strip
     static constexpr int PITCH = WAVE_NT + 2;                    // smem pitch of one parity row (pad on each side)
 };
 
 struct WaveParams {
-    const double *phi_in;
+    const double *phi_in;   // single-pass launches; a PEER launch derives both per pass from peer.buf[]
     double *phi_out;
     const double *D;
     int W, H;            // global grid
@@ -52,8 +63,16 @@ struct WaveParams {
     int grow0;           // global row of local row 0 of the arrays
     int nchunks;         // row chunks (not counting the short last chunk of a PEER pass)
     SorW w;
-    unsigned long long *slots;  // per-sweep max, TS entries used
-    WavePeer peer;              // fused ghost-row exchange (PEER kernels only)
+    unsigned long long *slots;  // per-sweep max: TS entries per pass
+    WavePeer peer;              // persistent multi-pass launch + fused ghost-row exchange (PEER kernels only)
+};
+
+// what changes from pass to pass inside one launch
+struct WaveDyn {
+    const double *phi_in;
+    double *phi_out;
+    double *up_out, *dn_out;     // the neighbouring slabs' output fields (nullptr: no neighbour)
+    unsigned long long *slots;
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
@@ -64,27 +83,33 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// thread 0 of a CTA that is about to read ghost rows: wait until the neighbour's pass `want` has delivered them
-__device__ __forceinline__ void peer_wait(const unsigned *flag, unsigned want, int *err) {
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// one thread: wait until *flag has reached `want` (sequence numbers only grow).  SYS: the flag is written by another
+// GPU.  A writer that never shows up must not hang the device: after ~3 s the slab's error word is set instead.
+template <bool SYS>
+__device__ __forceinline__ void seq_wait(const unsigned *flag, unsigned want, int *err) {
     const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(flag) - want) < 0) {
-        if (clock64() - t0 > 6000000000ll) {  // ~3 s: a neighbour died; report instead of hanging the GPU
+    while ((int)((SYS ? ld_acquire_sys(flag) : ld_acquire_gpu(flag)) - want) < 0) {
+        if (clock64() - t0 > 6000000000ll) {
             atomicExch(err, 1);
             break;
         }
-        __nanosleep(64);
+        __nanosleep(SYS ? 64 : 20);
     }
 }
-// all threads of the CTA: the edge rows of this CTA are stored; the last of the n_ctas CTAs raises the neighbour's flag
-__device__ __forceinline__ void peer_signal(unsigned *cnt, unsigned *sig, unsigned seq, unsigned n_ctas) {
+// all threads of the CTA: the edge rows of this CTA's strip are stored in the neighbour's field; raise its flag there
+__device__ __forceinline__ void strip_signal(unsigned *flag, unsigned seq) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
-        if (atomicAdd(cnt, 1u) == n_ctas - 1) {
-            atomicExch(cnt, 0u);
-            __threadfence_system();
-            st_release_sys(sig, seq);
-        }
+        st_release_sys(flag, seq);
     }
 }
 
@@ -98,7 +123,7 @@ struct WaveThread {  // per-thread invariants
 // One row step.  C = (f - ys) mod R is compile-time; chunks start so that the active cell of row r in phase ph
 // has window parity (r - ys + 1 + ph) & 1, i.e. (C + ph) & 1 for the row f-1-2ph updated at offset C.
 template <int TS, int C, bool STEADY, bool PEER>
-__device__ __forceinline__ void wave_step(const WaveParams &p, const WaveThread &t, const int f,
+__device__ __forceinline__ void wave_step(const WaveParams &p, const WaveDyn &d, const WaveThread &t, const int f,
                                           double (&v)[WaveCfg<TS>::R][2], double *__restrict__ sphi,
                                           double *__restrict__ sD, double (&lmax)[TS]) {
     using Cfg = WaveCfg<TS>;
@@ -112,8 +137,8 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveThread 
         const size_t base = row_ok ? (size_t)(fr - p.grow0) * W : 0;
         const bool a0 = row_ok && t.ex0, a1 = row_ok && t.ex1;
         const size_t o0 = a0 ? base + t.gx0 : 0, o1 = a1 ? base + t.gx0 + 1 : 0;
-        __pipeline_memcpy_async(sphi + (SL * 2 + 0) * PITCH + 1 + k, p.phi_in + o0, 8, a0 ? 0 : 8);
-        __pipeline_memcpy_async(sphi + (SL * 2 + 1) * PITCH + 1 + k, p.phi_in + o1, 8, a1 ? 0 : 8);
+        __pipeline_memcpy_async(sphi + (SL * 2 + 0) * PITCH + 1 + k, d.phi_in + o0, 8, a0 ? 0 : 8);
+        __pipeline_memcpy_async(sphi + (SL * 2 + 1) * PITCH + 1 + k, d.phi_in + o1, 8, a1 ? 0 : 8);
         __pipeline_memcpy_async(sD + (SL * 2 + 0) * PITCH + 1 + k, p.D + o0, 8, a0 ? 0 : 8);
         __pipeline_memcpy_async(sD + (SL * 2 + 1) * PITCH + 1 + k, p.D + o1, 8, a1 ? 0 : 8);
         __pipeline_commit();
@@ -146,9 +171,9 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveThread 
         const int r = f - 1 - 2 * ph;
         const double own = v[SL][q ^ 1];
         const double l = q ? own : nbv[ph], rr = q ? nbv[ph] : own;
-        const double u = v[SU][q], d = v[SD][q];
+        const double u = v[SU][q], dn = v[SD][q];
         const double val = v[SL][q];
-        const double sum = ((l + u) + rr) + d;  // ghost rows / columns read 0.0: identical to skipping them
+        const double sum = ((l + u) + rr) + dn;  // ghost rows / columns read 0.0: identical to skipping them
         double delta;
         if (!STEADY && (r == 0 || r == H - 1)) {  // CTA-uniform: domain top / bottom row
             const int cnt = (int)t.cx[q] - (r == 0 ? 1 : 0) - (r == H - 1 ? 1 : 0);
@@ -177,15 +202,15 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveThread 
         if (t.core && (STEADY || (r >= t.y0 && r < t.y1))) {
             const size_t o = (size_t)(r - p.grow0) * W + t.gx0;
             if (t.ex0 && t.ex1 && ((W & 1) == 0)) {
-                *reinterpret_cast<double2 *>(p.phi_out + o) = make_double2(v[SL][0], v[SL][1]);
+                *reinterpret_cast<double2 *>(d.phi_out + o) = make_double2(v[SL][0], v[SL][1]);
             } else {
-                if (t.ex0) p.phi_out[o] = v[SL][0];
-                if (t.ex1) p.phi_out[o + 1] = v[SL][1];
+                if (t.ex0) d.phi_out[o] = v[SL][0];
+                if (t.ex1) d.phi_out[o + 1] = v[SL][1];
             }
             if constexpr (PEER && !STEADY) {  // rows next to a slab edge also go to the neighbour's ghost rows
                 double *dst = nullptr;
-                if (p.peer.up_out && r < p.row_first + p.peer.gh) dst = p.peer.up_out + (size_t)(r - p.peer.up_grow0) * W + t.gx0;
-                if (p.peer.dn_out && r >= p.row_first + p.rows - p.peer.gh) dst = p.peer.dn_out + (size_t)(r - p.peer.dn_grow0) * W + t.gx0;
+                if (d.up_out && r < p.row_first + p.peer.gh) dst = d.up_out + (size_t)(r - p.peer.up_grow0) * W + t.gx0;
+                if (d.dn_out && r >= p.row_first + p.rows - p.peer.gh) dst = d.dn_out + (size_t)(r - p.peer.dn_grow0) * W + t.gx0;
                 if (dst) {
                     if (t.ex0) dst[0] = v[SL][0];
                     if (t.ex1) dst[1] = v[SL][1];
@@ -200,62 +225,23 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveThread 
 
 template <int TS, int C, bool STEADY, bool PEER>
 struct WaveUnroll {
-    static __device__ __forceinline__ void run(const WaveParams &p, const WaveThread &t, const int f, const int f_last,
-                                               double (&v)[WaveCfg<TS>::R][2], double *sphi, double *sD, double (&lmax)[TS]) {
+    static __device__ __forceinline__ void run(const WaveParams &p, const WaveDyn &d, const WaveThread &t, const int f,
+                                               const int f_last, double (&v)[WaveCfg<TS>::R][2], double *sphi, double *sD,
+                                               double (&lmax)[TS]) {
         if (!STEADY && f + C > f_last) return;  // CTA-uniform: the chunk's last block stops at its last step
-        wave_step<TS, C, STEADY, PEER>(p, t, f + C, v, sphi, sD, lmax);
-        if constexpr (C + 1 < WaveCfg<TS>::R) WaveUnroll<TS, C + 1, STEADY, PEER>::run(p, t, f, f_last, v, sphi, sD, lmax);
+        wave_step<TS, C, STEADY, PEER>(p, d, t, f + C, v, sphi, sD, lmax);
+        if constexpr (C + 1 < WaveCfg<TS>::R) WaveUnroll<TS, C + 1, STEADY, PEER>::run(p, d, t, f, f_last, v, sphi, sD, lmax);
     }
 };
 
+// One pass of one CTA over its chunk.  top / bot: this chunk touches the slab's first / last owned rows AND a
+// neighbouring slab is attached there (its ghost rows are fed from here, flag value `seq`).
 template <int TS, bool PEER>
-__global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __grid_constant__ WaveParams p) {
+__device__ __forceinline__ void wave_chunk(const WaveParams &p, const WaveDyn &d, const WaveThread &t, double *sphi, double *sD,
+                                           double (*wred)[WAVE_NT / 32], const bool top, const bool bot, const unsigned seq) {
     using Cfg = WaveCfg<TS>;
     constexpr int R = Cfg::R, NP = Cfg::NP, PITCH = Cfg::PITCH;
-    extern __shared__ double smem[];
-    double *sphi = smem;                   // [R][2][PITCH]
-    double *sD = smem + R * 2 * PITCH;     // [R][2][PITCH]
-    __shared__ double wred[TS][WAVE_NT / 32];
-
-    WaveThread t;
-    t.k = threadIdx.x;
-    const int W = p.W, H = p.H;
-    const int xw0 = blockIdx.x * Cfg::CORE - Cfg::HX;              // window origin (global x, even)
-    if (PEER && p.peer.tail_rows > 0 && blockIdx.y == gridDim.y - 1) {  // short last chunk: the bottom edge rows leave early
-        t.y1 = p.row_first + p.rows;
-        t.y0 = t.y1 - p.peer.tail_rows;
-    } else {
-        const int main_rows = p.rows - (PEER ? p.peer.tail_rows : 0);   // balanced split: chunk lengths differ by <= 1 row
-        t.y0 = p.row_first + (int)blockIdx.y * main_rows / p.nchunks;
-        t.y1 = p.row_first + ((int)blockIdx.y + 1) * main_rows / p.nchunks;
-    }
-    if (t.y0 >= t.y1) return;
-    const bool top = PEER && t.y0 == p.row_first && p.peer.up_out != nullptr;
-    const bool bot = PEER && t.y1 == p.row_first + p.rows && p.peer.dn_out != nullptr;
-    if constexpr (PEER) {
-        if (threadIdx.x == 0) {
-            if (top) peer_wait(p.peer.wait_up, p.peer.seq - 1, p.peer.err);
-            if (bot) peer_wait(p.peer.wait_dn, p.peer.seq - 1, p.peer.err);
-        }
-    }
-    // first row streamed in: NP rows of warm-up, moved one row earlier when needed so that the colour parity of
-    // every (step offset, phase) pair is a compile-time constant: active parity of row r in phase ph is
-    // (xw0 + r + ph) & 1 = (r + ph) & 1, and r = ys + C - 1 - 2ph at offset C  =>  need ys odd
-    t.ys = t.y0 - NP;
-    if ((t.ys & 1) == 0) t.ys -= 1;
-    t.ye = t.y1 - 1 + NP;                                           // last row streamed in
-    t.gx0 = xw0 + 2 * t.k;
-    t.ex0 = t.gx0 >= 0 && t.gx0 < W;
-    t.ex1 = t.gx0 + 1 >= 0 && t.gx0 + 1 < W;
-    t.core = (2 * t.k >= Cfg::HX) && (2 * t.k < Cfg::LXW - Cfg::HX);
-    {
-        const int c0 = 4 - (t.gx0 == 0 ? 1 : 0) - (t.gx0 == W - 1 ? 1 : 0), c1 = 4 - (t.gx0 + 1 == 0 ? 1 : 0) - (t.gx0 + 1 == W - 1 ? 1 : 0);
-        t.cx[0] = (double)c0; t.cx[1] = (double)c1;
-        t.wx[0] = wsel(p.w, c0); t.wx[1] = wsel(p.w, c1);
-    }
-    for (int i = t.k; i < 2 * R * 2 * PITCH; i += WAVE_NT) smem[i] = 0.0;
-    __syncthreads();
-
+    const int H = p.H;
     double v[R][2];
 #pragma unroll
     for (int i = 0; i < R; ++i) { v[i][0] = 0.0; v[i][1] = 0.0; }
@@ -268,11 +254,11 @@ __global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __gr
     for (int j = 0; j < WAVE_PF; ++j) {
         const int fr = t.ys + j;
         const bool row_ok = fr <= t.ye && fr >= 0 && fr < H;
-        const size_t base = row_ok ? (size_t)(fr - p.grow0) * W : 0;
+        const size_t base = row_ok ? (size_t)(fr - p.grow0) * p.W : 0;
         const bool a0 = row_ok && t.ex0, a1 = row_ok && t.ex1;
         const size_t o0 = a0 ? base + t.gx0 : 0, o1 = a1 ? base + t.gx0 + 1 : 0;
-        __pipeline_memcpy_async(sphi + (j * 2 + 0) * PITCH + 1 + t.k, p.phi_in + o0, 8, a0 ? 0 : 8);
-        __pipeline_memcpy_async(sphi + (j * 2 + 1) * PITCH + 1 + t.k, p.phi_in + o1, 8, a1 ? 0 : 8);
+        __pipeline_memcpy_async(sphi + (j * 2 + 0) * PITCH + 1 + t.k, d.phi_in + o0, 8, a0 ? 0 : 8);
+        __pipeline_memcpy_async(sphi + (j * 2 + 1) * PITCH + 1 + t.k, d.phi_in + o1, 8, a1 ? 0 : 8);
         __pipeline_memcpy_async(sD + (j * 2 + 0) * PITCH + 1 + t.k, p.D + o0, 8, a0 ? 0 : 8);
         __pipeline_memcpy_async(sD + (j * 2 + 1) * PITCH + 1 + t.k, p.D + o1, 8, a1 ? 0 : 8);
         __pipeline_commit();
@@ -291,18 +277,18 @@ __global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __gr
             if (top && r_min < p.row_first + p.peer.gh) steady = false;
             if (bot && r_min + R - 1 >= p.row_first + p.rows - p.peer.gh) steady = false;
         }
-        if (steady) WaveUnroll<TS, 0, true, PEER>::run(p, t, fb, f_last, v, sphi, sD, lmax);
-        else WaveUnroll<TS, 0, false, PEER>::run(p, t, fb, f_last, v, sphi, sD, lmax);
+        if (steady) WaveUnroll<TS, 0, true, PEER>::run(p, d, t, fb, f_last, v, sphi, sD, lmax);
+        else WaveUnroll<TS, 0, false, PEER>::run(p, d, t, fb, f_last, v, sphi, sD, lmax);
         if constexpr (PEER) {  // the top edge rows are complete long before the chunk is: tell the upper neighbour now
             if (top && !up_sent && r_min + R - 1 >= p.row_first + p.peer.gh - 1) {
-                peer_signal(p.peer.cnt, p.peer.sig_up, p.peer.seq, gridDim.x);
+                strip_signal(p.peer.sig_up + blockIdx.x, seq);
                 up_sent = true;
             }
         }
     }
     if constexpr (PEER) {
-        if (top && !up_sent) peer_signal(p.peer.cnt, p.peer.sig_up, p.peer.seq, gridDim.x);
-        if (bot) peer_signal(p.peer.cnt + 1, p.peer.sig_dn, p.peer.seq, gridDim.x);
+        if (top && !up_sent) strip_signal(p.peer.sig_up + blockIdx.x, seq);
+        if (bot) strip_signal(p.peer.sig_dn + blockIdx.x, seq);
     }
 
     // publish the per-sweep maxima
@@ -318,7 +304,102 @@ __global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __gr
         for (int s = 0; s < TS; ++s) {
             double m = t.k < WAVE_NT / 32 ? wred[s][t.k] : 0.0;
             m = warp_max(m);
-            if (t.k == 0 && m > 0.0) atomicMax(p.slots + s, (unsigned long long)__double_as_longlong(m));
+            if (t.k == 0 && m > 0.0) atomicMax(d.slots + s, (unsigned long long)__double_as_longlong(m));
+        }
+    }
+}
+
+template <int TS, bool PEER>
+__global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __grid_constant__ WaveParams p) {
+    using Cfg = WaveCfg<TS>;
+    constexpr int R = Cfg::R, NP = Cfg::NP, PITCH = Cfg::PITCH;
+    extern __shared__ double smem[];
+    double *sphi = smem;                   // [R][2][PITCH]
+    double *sD = smem + R * 2 * PITCH;     // [R][2][PITCH]
+    __shared__ double wred[TS][WAVE_NT / 32];
+
+    WaveThread t;
+    t.k = threadIdx.x;
+    const int W = p.W;
+    const int xw0 = blockIdx.x * Cfg::CORE - Cfg::HX;              // window origin (global x, even)
+    if (PEER && p.peer.tail_rows > 0 && blockIdx.y == gridDim.y - 1) {  // short last chunk: the bottom edge rows leave early
+        t.y1 = p.row_first + p.rows;
+        t.y0 = t.y1 - p.peer.tail_rows;
+    } else {
+        const int main_rows = p.rows - (PEER ? p.peer.tail_rows : 0);   // balanced split: chunk lengths differ by <= 1 row
+        t.y0 = p.row_first + (int)blockIdx.y * main_rows / p.nchunks;
+        t.y1 = p.row_first + ((int)blockIdx.y + 1) * main_rows / p.nchunks;
+    }
+    const bool empty = t.y0 >= t.y1;
+    if (!PEER && empty) return;
+    // first row streamed in: NP rows of warm-up, moved one row earlier when needed so that the colour parity of
+    // every (step offset, phase) pair is a compile-time constant: active parity of row r in phase ph is
+    // (xw0 + r + ph) & 1 = (r + ph) & 1, and r = ys + C - 1 - 2ph at offset C  =>  need ys odd
+    t.ys = t.y0 - NP;
+    if ((t.ys & 1) == 0) t.ys -= 1;
+    t.ye = t.y1 - 1 + NP;                                           // last row streamed in
+    t.gx0 = xw0 + 2 * t.k;
+    t.ex0 = t.gx0 >= 0 && t.gx0 < W;
+    t.ex1 = t.gx0 + 1 >= 0 && t.gx0 + 1 < W;
+    t.core = (2 * t.k >= Cfg::HX) && (2 * t.k < Cfg::LXW - Cfg::HX);
+    {
+        const int c0 = 4 - (t.gx0 == 0 ? 1 : 0) - (t.gx0 == W - 1 ? 1 : 0), c1 = 4 - (t.gx0 + 1 == 0 ? 1 : 0) - (t.gx0 + 1 == W - 1 ? 1 : 0);
+        t.cx[0] = (double)c0; t.cx[1] = (double)c1;
+        t.wx[0] = wsel(p.w, c0); t.wx[1] = wsel(p.w, c1);
+    }
+    // the ring is zeroed once: a pass overwrites every slot it reads for a live result, and the two pad columns of a
+    // parity row are never written
+    for (int i = t.k; i < 2 * R * 2 * PITCH; i += WAVE_NT) smem[i] = 0.0;
+    __syncthreads();
+
+    if constexpr (!PEER) {
+        WaveDyn d;
+        d.phi_in = p.phi_in; d.phi_out = p.phi_out; d.up_out = nullptr; d.dn_out = nullptr; d.slots = p.slots;
+        wave_chunk<TS, false>(p, d, t, sphi, sD, wred, false, false, 0u);
+    } else {
+        // ---- persistent launch: p.peer.npass passes, CTAs synchronise with their neighbours only ----
+        const int nbx = (int)gridDim.x, nby = (int)gridDim.y, bx = (int)blockIdx.x, by = (int)blockIdx.y;
+        unsigned *const my_done = p.peer.done + by * nbx + bx;
+        const bool has_up = p.peer.up_buf[0] != nullptr, has_dn = p.peer.dn_buf[0] != nullptr;
+        const bool top = !empty && has_up && t.y0 == p.row_first;
+        const bool bot = !empty && has_dn && t.y1 == p.row_first + p.rows;
+        for (int i = 0; i < p.peer.npass; ++i) {
+            const unsigned seq = p.peer.seq0 + (unsigned)i + 1u;
+            const int oid = (p.peer.cur ^ (i & 1)) ^ 1;          // buffer this pass writes
+            WaveDyn d;
+            d.phi_in = p.peer.buf[oid ^ 1];
+            d.phi_out = p.peer.buf[oid];
+            d.up_out = has_up ? p.peer.up_buf[oid] : nullptr;
+            d.dn_out = has_dn ? p.peer.dn_buf[oid] : nullptr;
+            d.slots = p.slots + (size_t)i * TS;
+            // (1) dependencies of this pass.  Inside the GPU: the eight neighbouring CTAs have published pass seq-1 --
+            // the only ones whose output this CTA reads and whose input it is about to overwrite (the launch boundary
+            // covers the first pass).  Across GPUs: the neighbour's edge CTAs of strips bx-1..bx+1 have raised their
+            // flags for pass seq-1: their rows are in this slab's ghost rows, and they no longer read the ghost rows
+            // this pass overwrites over there.
+            {
+                const int tid = (int)threadIdx.x;
+                if (i > 0 && tid < 9 && tid != 4) {
+                    const int nx = bx + tid % 3 - 1, ny = by + tid / 3 - 1;
+                    if (nx >= 0 && nx < nbx && ny >= 0 && ny < nby) seq_wait<false>(p.peer.done + ny * nbx + nx, seq - 1u, p.peer.err);
+                } else if (tid >= 32 && tid < 35) {
+                    const int nx = bx + tid - 33;
+                    if (top && nx >= 0 && nx < nbx) seq_wait<true>(p.peer.wait_up + nx, seq - 1u, p.peer.err);
+                } else if (tid >= 64 && tid < 67) {
+                    const int nx = bx + tid - 65;
+                    if (bot && nx >= 0 && nx < nbx) seq_wait<true>(p.peer.wait_dn + nx, seq - 1u, p.peer.err);
+                }
+                __syncthreads();
+                __threadfence();   // every thread's loads of this pass are ordered behind the flags observed above
+            }
+            // (2) the pass
+            if (!empty) wave_chunk<TS, true>(p, d, t, sphi, sD, wred, top, bot, seq);
+            // (3) publish: every store of this CTA's pass is visible before its sequence word moves
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                st_release_gpu(my_done, seq);
+            }
         }
     }
 }
@@ -327,18 +408,23 @@ constexpr int TILED_TS = 2;
 int tiled_sweeps_per_pass() { return TILED_TS; }
 
 template <int TS, bool PEER>
+static int wave_smem_optin(size_t smem) {
+    // the opt-in is per device: remember which devices have it (contexts on several threads may race here: atomic)
+    static std::atomic<unsigned long long> done_mask{0ull};
+    int dev = 0;
+    PCD_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !((done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
+        PCD_CUDA(cudaFuncSetAttribute(sor_wave_kernel<TS, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
+    }
+    return PCD_OK;
+}
+
+template <int TS, bool PEER>
 static int launch_wave(const WaveParams &prm, int sm_count, int sm_reserve, cudaStream_t stream) {
     using Cfg = WaveCfg<TS>;
     const size_t smem = (size_t)2 * Cfg::R * 2 * Cfg::PITCH * sizeof(double);
-    {   // the opt-in is per device: remember which devices have it (contexts on several threads may race here: atomic)
-        static std::atomic<unsigned long long> done_mask{0ull};
-        int dev = 0;
-        PCD_CUDA(cudaGetDevice(&dev));
-        if (dev >= 64 || !((done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
-            PCD_CUDA(cudaFuncSetAttribute(sor_wave_kernel<TS, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
-        }
-    }
+    PCD_TRY((wave_smem_optin<TS, PEER>(smem)));
     WaveParams p = prm;
     const int strips = (p.W + Cfg::CORE - 1) / Cfg::CORE;
     // ONE wave of two CTAs per SM (never a second, nearly empty wave).  Measured on B200 (2048^2: 59 chunks of 35
@@ -354,14 +440,25 @@ static int launch_wave(const WaveParams &prm, int sm_count, int sm_reserve, cuda
     if constexpr (PEER) {
         // with a lower neighbour the bottom rows get a short chunk of their own (they are the LAST rows a chunk
         // walking down would finish), so that the neighbour has them long before the pass ends
-        if (p.peer.dn_out && p.rows >= 8 * min_rows && chunks >= 3) { tail = 2 * Cfg::NP + 4; chunks -= 1; }
+        if (p.peer.dn_buf[0] && p.rows >= 8 * min_rows && chunks >= 3) { tail = 2 * Cfg::NP + 4; chunks -= 1; }
         p.peer.tail_rows = tail;
     }
     const int main_rows = p.rows - tail;
     if (chunks * min_rows > main_rows) chunks = main_rows / min_rows;
     if (chunks < 1) chunks = 1;
     p.nchunks = chunks;
-    sor_wave_kernel<TS, PEER><<<dim3(strips, chunks + (tail ? 1 : 0)), WAVE_NT, smem, stream>>>(p);
+    const dim3 grid(strips, chunks + (tail ? 1 : 0));
+    if constexpr (PEER) {
+        // persistent: every CTA must be resident (they wait for each other)
+        if ((int)(grid.x * grid.y) > WAVE_CTAS * sm_count || (int)(grid.x * grid.y) > WAVE_MAX_CTAS) {
+            set_error("wavefront kernel: %u x %u CTAs cannot be co-resident on %d SMs", grid.x, grid.y, sm_count);
+            return PCD_ERR_UNSUPPORTED;
+        }
+        void *args[] = {&p};
+        PCD_CUDA(cudaLaunchCooperativeKernel((void *)sor_wave_kernel<TS, true>, grid, dim3(WAVE_NT), args, smem, stream));
+    } else {
+        sor_wave_kernel<TS, false><<<grid, WAVE_NT, smem, stream>>>(p);
+    }
     PCD_LAUNCHED();
     return PCD_OK;
 }
@@ -379,16 +476,19 @@ int tiled_pass(const double *phi_in, double *phi_out, const double *D, int W, in
     return launch_wave<1, false>(prm, sm_count, sm_reserve, stream);
 }
 
-// The same pass over a whole slab with the ghost-row exchange fused in (see WavePeer).
-int tiled_pass_peer(const double *phi_in, double *phi_out, const double *D, int W, int H, int row_first, int rows, int grow0,
-                    int nsweeps, unsigned long long *slots, const WavePeer &peer, int sm_count, int sm_reserve,
-                    cudaStream_t stream) {
+// ONE persistent launch: peer.npass passes of `sweeps_per_pass` (1 or TILED_TS) sweeps each over a whole slab, the field
+// ping-ponging between peer.buf[0] and peer.buf[1] (peer.cur holds it first), maxima into slots[0 .. npass *
+// sweeps_per_pass), ghost rows pushed into the attached neighbours (see WavePeer).
+int tiled_run_peer(const double *D, int W, int H, int row_first, int rows, int grow0, int sweeps_per_pass,
+                   unsigned long long *slots, const WavePeer &peer, int sm_count, int sm_reserve, cudaStream_t stream) {
     WaveParams prm;
-    prm.phi_in = phi_in; prm.phi_out = phi_out; prm.D = D; prm.W = W; prm.H = H;
+    prm.phi_in = nullptr; prm.phi_out = nullptr; prm.D = D; prm.W = W; prm.H = H;
     prm.row_first = row_first; prm.rows = rows; prm.grow0 = grow0; prm.nchunks = 1;
     prm.w = make_w(W); prm.slots = slots; prm.peer = peer;
-    if (nsweeps >= 2) return launch_wave<2, true>(prm, sm_count, sm_reserve, stream);
+    if (sweeps_per_pass >= 2) return launch_wave<2, true>(prm, sm_count, sm_reserve, stream);
     return launch_wave<1, true>(prm, sm_count, sm_reserve, stream);
 }
+
+int tiled_strips(int W) { return (W + WaveCfg<TILED_TS>::CORE - 1) / WaveCfg<TILED_TS>::CORE; }
 
 }  // namespace pcd

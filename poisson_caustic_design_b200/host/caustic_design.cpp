@@ -58,12 +58,14 @@ Caustic_design::Caustic_design(/* args */) {
     this->thickness = 0.0f;
     this->nthreads = 0;
     this->ctx = nullptr;
+    this->multi = nullptr;
     this->field_sync = SYNC_ALL;
     this->device = pcd_get_default_device();
     this->solver_path = PCD_SOLVER_AUTO;
 }
 
 Caustic_design::~Caustic_design() {
+    if (multi) pcd_multi_destroy(multi);   // before the context it is attached to
     if (ctx) pcd_destroy(ctx);
     delete mesh;  // the reference leaks its Mesh (src/caustic_design.cpp:16-18)
 }
@@ -176,6 +178,7 @@ void Caustic_design::initialize_solvers(std::vector<std::vector<double>> image) 
         if (row.size() != image[0].size()) throw std::invalid_argument("Input matrix has inconsistent row sizes.");
     if ((int)image.size() != resolution_y || (int)image[0].size() != resolution_x)
         throw std::invalid_argument("image size does not match set_domain_resolution");
+    if (multi) { pcd_multi_destroy(multi); multi = nullptr; }
     if (ctx) { pcd_destroy(ctx); ctx = nullptr; }
     pcd_config cfg{};
     cfg.mesh_res_x = mesh_res_x; cfg.mesh_res_y = mesh_res_y;
@@ -184,6 +187,10 @@ void Caustic_design::initialize_solvers(std::vector<std::vector<double>> image) 
     cfg.focal_l = focal_l; cfg.thickness = thickness;
     cfg.device = device; cfg.solver_path = solver_path;
     check(pcd_create(&cfg, &ctx), "initialize_solvers");
+    if (devices.size() > 1) {
+        check(pcd_multi_create(resolution_x, resolution_y, devices.data(), (int)devices.size(), &multi), "initialize_solvers (multi-GPU)");
+        check(pcd_multi_attach(multi, ctx), "initialize_solvers (multi-GPU)");
+    }
     std::vector<double> flat((size_t)resolution_x * resolution_y);
     for (int y = 0; y < resolution_y; ++y)
         for (int x = 0; x < resolution_x; ++x) flat[(size_t)y * resolution_x + x] = image[y][x];

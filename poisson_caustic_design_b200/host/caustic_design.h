@@ -15,6 +15,7 @@ typedef std::vector<double> point_t;
 typedef std::vector<point_t> polygon_t;
 
 struct pcd_ctx;
+struct pcd_multi;
 
 // src/mesh.h:33-104, reduced to what Caustic_design's callers use: the two point sets and the exporters.
 class Mesh {
@@ -93,12 +94,17 @@ class Caustic_design {
     void set_field_sync(FieldSync mode) { field_sync = mode; }
     void set_device(int device) { this->device = device; }
     void set_solver_path(int path) { solver_path = path; }
+    // Poisson solves spread over several GPUs of this process as row slabs; devices[0] also runs the other
+    // stages.  Bit-identical to one GPU.  Call before initialize_solvers; an empty list = single GPU.
+    void set_devices(const std::vector<int> &devices) { this->devices = devices; if (!devices.empty()) device = devices[0]; }
     void sync_fields();               // pull every public member from the device now
     void push_mesh();                 // upload mesh->target_points / source_points after the caller edited them
     int last_solver_sweeps() const;   // sweeps of the most recent Poisson solve
 
    private:
     pcd_ctx *ctx;
+    pcd_multi *multi;
+    std::vector<int> devices;
     FieldSync field_sync;
     int device;
     int solver_path;

@@ -40,6 +40,7 @@ extern "C" int pcd_host_parse_cli(int argc, const char *const *argv, pcd_cli_opt
     o->conv_tres = 0.01;             // :183
     o->device = 0;
     o->solver_path = PCD_SOLVER_AUTO;
+    o->gpus = 1;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "-h" || a == "--help") { o->help = 1; continue; }
@@ -65,10 +66,13 @@ extern "C" int pcd_host_parse_cli(int argc, const char *const *argv, pcd_cli_opt
         else if (name == "threads") ok = parse_int(value.c_str(), o->threads);
         else if (name == "conv_tres") ok = parse_float(value.c_str(), o->conv_tres);
         else if (name == "device") ok = parse_int(value.c_str(), o->device);
+        else if (name == "gpus") ok = parse_int(value.c_str(), o->gpus) && o->gpus >= 1;
         else if (name == "solver_path") {
             if (value == "auto") o->solver_path = PCD_SOLVER_AUTO;
             else if (value == "streaming") o->solver_path = PCD_SOLVER_STREAMING;
             else if (value == "resident") o->solver_path = PCD_SOLVER_RESIDENT;
+            else if (value == "tiled") o->solver_path = PCD_SOLVER_TILED;
+            else if (value == "dct") o->solver_path = PCD_SOLVER_DCT;   // opt-in direct backend
             else ok = false;
         } else { pcdh::g_host_err = "Flag could not be matched: " + name; return 1; }
         if (!ok) { pcdh::g_host_err = "Argument '" + name + "' received invalid value type '" + value + "'"; return 1; }

@@ -1,7 +1,7 @@
 // CLI drop-in for the reference's main.cpp:137-272: same flags, defaults, stdout lines and output files
 // (<output>output.obj, <output>heightmap.json, optional <progress_out>parameterization_<k>.svg / inverted.svg);
 // the transport and height loops run on the GPU through class Caustic_design (host/caustic_design.h).
-// Extra flags (--device N, --solver_path auto|streaming|resident, --quiet) do not change any default.
+// Extra flags (--device N, --gpus N, --solver_path auto|streaming|resident|tiled|dct, --quiet) do not change any default.
 #include <cmath>
 #include <cstdio>
 #include <iostream>
@@ -26,7 +26,8 @@ static void usage() {
                  "      --threads=[max_threads]           Number of CPU threads to use (ignored: GPU path)\n"
                  "      --conv_tres=[convergence]         Contrast convergence treshold\n"
                  "      --device=[n]                      CUDA device ordinal (default 0)\n"
-                 "      --solver_path=[auto|streaming|resident]\n";
+                 "      --gpus=[n]                        Poisson solves as row slabs on n GPUs (devices device..device+n-1)\n"
+                 "      --solver_path=[auto|streaming|resident|tiled|dct]\n";
 }
 
 int main(int argc, char const *argv[]) {
@@ -57,6 +58,11 @@ int main(int argc, char const *argv[]) {
     pcd_set_default_device(opt.device);
     Caustic_design caustic_design;
     caustic_design.set_solver_path(opt.solver_path);
+    if (opt.gpus > 1) {   // one process, several GPUs: row slabs with the ghost-row exchange inside the pass kernel
+        std::vector<int> devices;
+        for (int g = 0; g < opt.gpus; ++g) devices.push_back(opt.device + g);
+        caustic_design.set_devices(devices);
+    }
     // the CLI only needs the mesh between iterations (SVG progress) and h at the end
     caustic_design.set_field_sync(Caustic_design::SYNC_VERTEX);
 

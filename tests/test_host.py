@@ -18,7 +18,7 @@ class CliOptions(C.Structure):
     _fields_ = [("input_png", C.c_char * 1024), ("progress_out", C.c_char * 1024), ("output", C.c_char * 1024),
                 ("has_progress_out", C.c_int), ("res_w", C.c_int), ("mesh_width", C.c_double), ("focal_l", C.c_double),
                 ("thickness", C.c_double), ("conv_tres", C.c_double), ("threads", C.c_int), ("help", C.c_int),
-                ("device", C.c_int), ("solver_path", C.c_int), ("quiet", C.c_int)]
+                ("device", C.c_int), ("solver_path", C.c_int), ("quiet", C.c_int), ("gpus", C.c_int)]
 
 
 @pytest.fixture(scope="module")
