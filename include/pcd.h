@@ -187,6 +187,7 @@ void pcd_slab_destroy(pcd_slab *s);
 int pcd_slab_set_sm_reserve(pcd_slab *s, int n);   /* SMs this slab's pass kernels leave free for the collective's kernels (default 0) */
 int pcd_slab_device_ptrs(pcd_slab *s, void **phi0_dev, void **phi1_dev, void **sweep_max_dev);
 int pcd_slab_current(const pcd_slab *s);   /* which of the two phi buffers holds the field */
+int pcd_slab_error_word(pcd_slab *s, void **err_dev);   /* device address of the int error word (see pcd_slab_peer_status) */
 int pcd_slab_has_nan(const pcd_slab *s);   /* D (owned rows and their neighbours) contains NaN */
 int pcd_slab_upload(pcd_slab *s, const double *D_rows_with_ghosts, const double *phi_rows_with_ghosts);
 int pcd_slab_download(pcd_slab *s, double *phi_owned_rows);
@@ -197,6 +198,7 @@ int pcd_slab_pass(pcd_slab *s, int nsweeps, int slot);
 int pcd_slab_pass_part(pcd_slab *s, int nsweeps, int slot, int row_begin, int row_count, void *cuda_stream);
 int pcd_slab_flip(pcd_slab *s);
 int pcd_slab_clear_max(pcd_slab *s, int n_slots);
+int pcd_slab_clear_max_range(pcd_slab *s, int first_slot, int n_slots);
 /* D and phi of the slab (ghost rows included) from / owned rows of phi back to full width x height DEVICE arrays
  * on the slab's device (device-to-device, on the slab's stream; load waits for it) */
 int pcd_slab_load_device(pcd_slab *s, const double *D_full_dev, const double *phi_full_dev);

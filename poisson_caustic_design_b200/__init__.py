@@ -106,8 +106,10 @@ ABI = [
     ("pcd_slab_ghost_rows", C.c_int, []),
     ("pcd_slab_sweeps_per_pass", C.c_int, []),
     ("pcd_slab_current", C.c_int, [C.c_void_p]),
+    ("pcd_slab_error_word", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     ("pcd_slab_has_nan", C.c_int, [C.c_void_p]),
     ("pcd_slab_clear_max", C.c_int, [C.c_void_p, C.c_int]),
+    ("pcd_slab_clear_max_range", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("pcd_slab_load_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pcd_slab_store_device", C.c_int, [C.c_void_p, C.c_void_p]),
     ("pcd_set_solve_hook", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -22,8 +22,12 @@ struct pcd_multi {
     std::vector<pcd_slab *> slabs;
     std::vector<cudaStream_t> streams;          // one per slab; slabs on the same device share one
     std::vector<bool> owns_stream;
-    std::vector<unsigned long long *> h_max;    // pinned, 4096 per slab
+    std::vector<unsigned long long *> h_max;    // pinned, 4096 per slab: two blocks in flight (low / high half)
     std::vector<unsigned long long *> d_max;    // the slabs' per-sweep maxima (device)
+    std::vector<int *> d_err;                   // the slabs' error words (device)
+    std::vector<int *> h_err;                   // pinned, 2 per slab
+    std::vector<cudaStream_t> aux;              // per slab: copies a block's maxima out while the next block runs
+    std::vector<cudaEvent_t> ev_blk, ev_copied; // 2 per slab
     bool shared_devices = false;
     bool peers = false;                          // every slab thick enough for the fused exchange
     pcd_solver fallback;                         // single-GPU solver on devices[0]: NaN holes, slabs too thin
@@ -73,9 +77,27 @@ int pcd_multi_create(int width, int height, const int *devices, int n_devices, p
         void *mx = nullptr;
         pcd_slab_device_ptrs(s, nullptr, nullptr, &mx);
         m->d_max.push_back(static_cast<unsigned long long *>(mx));
+        void *ew = nullptr;
+        pcd_slab_error_word(s, &ew);
+        m->d_err.push_back(static_cast<int *>(ew));
         unsigned long long *h = nullptr;
-        if (cudaMallocHost(&h, sizeof(unsigned long long) * 4096) != cudaSuccess) { set_error("pcd_multi_create: pinned allocation failed"); rc = PCD_ERR_CUDA; break; }
+        int *he = nullptr;
+        cudaStream_t ax = nullptr;
+        if (cudaMallocHost(&h, sizeof(unsigned long long) * 4096) != cudaSuccess || cudaMallocHost(&he, sizeof(int) * 2) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ax, cudaStreamNonBlocking) != cudaSuccess) {
+            set_error("pcd_multi_create: pinned allocation / stream creation failed");
+            rc = PCD_ERR_CUDA;
+            break;
+        }
+        he[0] = he[1] = 0;
         m->h_max.push_back(h);
+        m->h_err.push_back(he);
+        m->aux.push_back(ax);
+        for (int i = 0; i < 4; ++i) {
+            cudaEvent_t ev = nullptr;
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { set_error("pcd_multi_create: event creation failed"); rc = PCD_ERR_CUDA; break; }
+            (i < 2 ? m->ev_blk : m->ev_copied).push_back(ev);
+        }
     }
     if (rc == PCD_OK && m->peers)
         for (int g = 0; g + 1 < n_devices && rc == PCD_OK; ++g) {
@@ -107,6 +129,10 @@ void pcd_multi_destroy(pcd_multi *m) {
     for (size_t g = 0; g < m->streams.size(); ++g)
         if (m->owns_stream[g] && m->streams[g]) { cudaSetDevice(m->dev[g]); cudaStreamDestroy(m->streams[g]); }
     for (unsigned long long *h : m->h_max) cudaFreeHost(h);
+    for (int *h : m->h_err) cudaFreeHost(h);
+    for (size_t g = 0; g < m->aux.size(); ++g) { cudaSetDevice(m->dev[g]); cudaStreamDestroy(m->aux[g]); }
+    for (cudaEvent_t e : m->ev_blk) cudaEventDestroy(e);
+    for (cudaEvent_t e : m->ev_copied) cudaEventDestroy(e);
     if (m->fallback_ready) { cudaSetDevice(m->dev[0]); solver_free(&m->fallback); }
     delete m;
 }
@@ -114,7 +140,7 @@ void pcd_multi_destroy(pcd_multi *m) {
 int pcd_multi_set_check_every(pcd_multi *m, int sweeps) {
     if (!m || sweeps < 1) { set_error("pcd_multi_set_check_every: bad arguments"); return PCD_ERR_INVALID; }
     const int TS = pcd_slab_sweeps_per_pass();
-    m->check_every = sweeps > 4096 ? 4096 : (sweeps + TS - 1) / TS * TS;
+    m->check_every = sweeps > 2048 ? 2048 : (sweeps + TS - 1) / TS * TS;
     return PCD_OK;
 }
 
@@ -150,38 +176,56 @@ int pcd_multi_solve(pcd_multi *m, const double *D_dev, double *phi_dev, int max_
     PCD_CUDA(cudaEventCreate(&e0));
     PCD_CUDA(cudaEventCreate(&e1));
     PCD_CUDA(cudaEventRecord(e0, m->streams[0]));
-    int done = 0, conv = 0;
+    // Blocks of check_every sweeps; the stopping rule is evaluated ONE BLOCK LATE (block b+1 is queued before the maxima
+    // of block b are read; they leave on the slabs' side streams), so no GPU drains between blocks.  Same schedule as
+    // the single-GPU large-grid solver (run_tiled) => same bits.
+    constexpr int HALF = 2048;
+    int launched = 0, done = 0, conv = 0, blk = 0, head = 0, npend = 0;
+    int pend_k[2] = {0, 0}, pend_first[2] = {0, 0};
     double last = 0.0;
-    while (done < max_iterations && !conv) {
-        const int k = max_iterations - done < m->check_every ? max_iterations - done : m->check_every;
-        for (int g = 0; g < n; ++g) PCD_TRY(pcd_slab_clear_max(m->slabs[g], k));
-        if (m->shared_devices) {     // slabs of one device run one after the other: advance all slabs pass by pass
-            for (int j = 0; j < k; j += TS)
-                for (int g = 0; g < n; ++g) PCD_TRY(pcd_slab_peer_run(m->slabs[g], k - j < TS ? k - j : TS, j));
-        } else {                     // one persistent launch per slab for the whole block
-            for (int g = 0; g < n; ++g) PCD_TRY(pcd_slab_peer_run(m->slabs[g], k, 0));
+    for (;;) {
+        if (launched < max_iterations && !conv && npend < 2) {
+            const int k = max_iterations - launched < m->check_every ? max_iterations - launched : m->check_every;
+            const int b = blk & 1, off = b * HALF;
+            for (int g = 0; g < n; ++g) PCD_TRY(pcd_slab_clear_max_range(m->slabs[g], off, k));
+            if (m->shared_devices) {     // slabs of one device run one after the other: advance all slabs pass by pass
+                for (int j = 0; j < k; j += TS)
+                    for (int g = 0; g < n; ++g) PCD_TRY(pcd_slab_peer_run(m->slabs[g], k - j < TS ? k - j : TS, off + j));
+            } else {                     // one persistent launch per slab for the whole block
+                for (int g = 0; g < n; ++g) PCD_TRY(pcd_slab_peer_run(m->slabs[g], k, off));
+            }
+            info->launches += m->shared_devices ? n * ((k + TS - 1) / TS) : n * (1 + (k % TS ? 1 : 0));
+            for (int g = 0; g < n; ++g) {
+                PCD_TRY(select_device(m->dev[g]));
+                PCD_CUDA(cudaEventRecord(m->ev_blk[2 * g + b], m->streams[g]));
+                PCD_CUDA(cudaStreamWaitEvent(m->aux[g], m->ev_blk[2 * g + b], 0));
+                PCD_CUDA(cudaMemcpyAsync(m->h_max[g] + off, m->d_max[g] + off, sizeof(unsigned long long) * k, cudaMemcpyDeviceToHost, m->aux[g]));
+                PCD_CUDA(cudaMemcpyAsync(m->h_err[g] + b, m->d_err[g], sizeof(int), cudaMemcpyDeviceToHost, m->aux[g]));
+                PCD_CUDA(cudaEventRecord(m->ev_copied[2 * g + b], m->aux[g]));
+            }
+            pend_k[b] = k; pend_first[b] = launched;
+            launched += k; ++blk; ++npend;
+            continue;
         }
-        info->launches += n * ((k + TS - 1) / TS);
+        if (!npend) break;
+        const int b = head & 1, off = b * HALF, k = pend_k[b];
         for (int g = 0; g < n; ++g) {
             PCD_TRY(select_device(m->dev[g]));
-            PCD_CUDA(cudaMemcpyAsync(m->h_max[g], m->d_max[g], sizeof(unsigned long long) * k, cudaMemcpyDeviceToHost, m->streams[g]));
+            PCD_CUDA(cudaEventSynchronize(m->ev_copied[2 * g + b]));
+            if (m->h_err[g][b]) { set_error("pcd_multi_solve: slab %d gave up waiting for a neighbour's ghost rows", g); return PCD_ERR_CUDA; }
         }
-        for (int g = 0; g < n; ++g) {
-            int timed_out = 0;
-            PCD_TRY(pcd_slab_peer_status(m->slabs[g], &timed_out));   // waits for the slab's stream
-            if (timed_out) { set_error("pcd_multi_solve: slab %d gave up waiting for a neighbour's ghost rows", g); return PCD_ERR_CUDA; }
-        }
-        for (int j = 0; j < k; ++j) {
+        for (int j = 0; j < k && !conv; ++j) {
             double mx = 0.0;
             for (int g = 0; g < n; ++g) {
                 double v;
-                memcpy(&v, &m->h_max[g][j], sizeof(double));
+                memcpy(&v, &m->h_max[g][off + j], sizeof(double));
                 if (v > mx) mx = v;
             }
-            if (!conv && mx < tol) { conv = done + j + 1; last = mx; }
-            if (!conv && j == k - 1) last = mx;
+            if (mx < tol) conv = pend_first[b] + j + 1;
+            if (conv || j == k - 1) last = mx;
         }
-        done += k;
+        done = pend_first[b] + k;
+        ++head; --npend;
     }
     for (int g = 0; g < n; ++g) PCD_TRY(pcd_slab_store_device(m->slabs[g], phi_dev));
     for (int g = 0; g < n; ++g) {

@@ -74,6 +74,8 @@ struct WavePeer {
     int *err = nullptr;                                       // local: set when a wait ran into its time limit
     unsigned seq0 = 0;                                        // sequence number of the last pass before this launch
     int tail_rows = 0;                                        // rows of the short last chunk (filled by the launcher)
+    unsigned long long *trace = nullptr;                      // diagnostics (PCD_WAVE_TRACE): per CTA and pass 4 x globaltimer
+                                                              // [wait begin, pass begin, pass end, published], else nullptr
 };
 int tiled_run_peer(const double *D, int W, int H, int row_first, int rows, int grow0, int sweeps_per_pass,
                    unsigned long long *slots, const WavePeer &peer, int sm_count, int sm_reserve, cudaStream_t stream);

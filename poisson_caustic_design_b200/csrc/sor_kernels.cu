@@ -137,74 +137,95 @@ static int run_streaming(pcd_solver *s, const double *D, double *phi, int max_it
 // Tiled path (sor_tiled.cu): TS sweeps per pass, ping-pong between phi and a second buffer.  A block of `chunk` sweeps
 // between two convergence tests is ONE persistent launch (the CTAs synchronise with their neighbours between passes, no
 // kernel boundary); PCD_WAVE_LAUNCH_PER_PASS=1 restores one launch per pass (diagnostics).
+// The stopping rule is evaluated ONE BLOCK LATE: block b+1 is queued before the maxima of block b are read (they are
+// copied out on a side stream), so the device never drains between blocks.  A solve that meets the rule in block b
+// therefore also executes block b+1 -- the same schedule as the multi-GPU slab solvers (slab.py, multi_gpu.cu), which
+// is what makes an N-GPU solve bit-identical to this one.
 static int run_tiled(pcd_solver *s, const double *D, double *phi, int max_it, double tol, pcd_solve_info *info) {
     const int W = s->W, H = s->H;
     const int TS = tiled_sweeps_per_pass();
+    constexpr int HALF = 2048;   // the slot ring / pinned mirror hold two blocks in flight
     if (!s->phi_alt) PCD_CUDA(cudaMalloc(&s->phi_alt, sizeof(double) * (size_t)W * H));
     static const bool per_pass = getenv("PCD_WAVE_LAUNCH_PER_PASS") != nullptr;
-    if (!per_pass && !s->wave_ctl) {
+    if (!s->wave_ctl) {
         PCD_CUDA(cudaMalloc(&s->wave_ctl, sizeof(unsigned) * (WAVE_MAX_CTAS + 16)));
         PCD_CUDA(cudaMemsetAsync(s->wave_ctl, 0, sizeof(unsigned) * (WAVE_MAX_CTAS + 16), s->stream));
+        PCD_CUDA(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            PCD_CUDA(cudaEventCreateWithFlags(&s->ev_blk[i], cudaEventDisableTiming));
+            PCD_CUDA(cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming));
+        }
     }
     int chunk = s->check_lag > 0 ? s->check_lag : 64;
     chunk = ((chunk + TS - 1) / TS) * TS;  // whole passes
-    if (chunk > 4096) chunk = 4096;
+    if (chunk > HALF) chunk = HALF;
     double *buf[2] = {phi, s->phi_alt};
     int cur = 0;
-    int done = 0, conv = 0;
+    int launched = 0, done = 0, conv = 0, blk = 0, head = 0, npend = 0;
+    int pend_k[2] = {0, 0}, pend_first[2] = {0, 0};
     double last = 0.0;
-    while (done < max_it && !conv) {
-        const int k = max_it - done < chunk ? max_it - done : chunk;
-        PCD_CUDA(cudaMemsetAsync(s->sweep_max, 0, sizeof(unsigned long long) * k, s->stream));
-        PCD_CUDA(cudaEventRecord(s->evk0, s->stream));
-        for (int j = 0; j < k;) {
-            if (per_pass) {
-                const int ns = k - j < TS ? k - j : TS;
-                PCD_TRY(tiled_pass(buf[cur], buf[cur ^ 1], D, W, H, 0, H, 0, ns, s->sweep_max + j, s->sm_count, 0, s->stream));
-                cur ^= 1;
-                j += ns;
-            } else {
-                const int spp = k - j >= TS ? TS : 1;
-                const int npass = k - j >= TS ? (k - j) / TS : k - j;
-                WavePeer pr;
-                pr.buf[0] = buf[0]; pr.buf[1] = buf[1];
-                pr.cur = cur;
-                pr.npass = npass;
-                pr.done = s->wave_ctl;
-                pr.err = reinterpret_cast<int *>(s->wave_ctl + WAVE_MAX_CTAS);
-                pr.seq0 = s->wave_seq;
-                PCD_TRY(tiled_run_peer(D, W, H, 0, H, 0, spp, s->sweep_max + j, pr, s->sm_count, 0, s->stream));
-                s->wave_seq += (unsigned)npass;
-                cur ^= (npass & 1);
-                j += npass * spp;
+    PCD_CUDA(cudaEventRecord(s->evk0, s->stream));
+    for (;;) {
+        if (launched < max_it && !conv && npend < 2) {
+            const int k = max_it - launched < chunk ? max_it - launched : chunk;
+            const int b = blk & 1, off = b * HALF;
+            PCD_CUDA(cudaMemsetAsync(s->sweep_max + off, 0, sizeof(unsigned long long) * k, s->stream));
+            for (int j = 0; j < k;) {
+                if (per_pass) {
+                    const int ns = k - j < TS ? k - j : TS;
+                    PCD_TRY(tiled_pass(buf[cur], buf[cur ^ 1], D, W, H, 0, H, 0, ns, s->sweep_max + off + j, s->sm_count, 0, s->stream));
+                    cur ^= 1;
+                    j += ns;
+                } else {
+                    const int spp = k - j >= TS ? TS : 1;
+                    const int npass = k - j >= TS ? (k - j) / TS : k - j;
+                    WavePeer pr;
+                    pr.buf[0] = buf[0]; pr.buf[1] = buf[1];
+                    pr.cur = cur;
+                    pr.npass = npass;
+                    pr.done = s->wave_ctl;
+                    pr.err = reinterpret_cast<int *>(s->wave_ctl + WAVE_MAX_CTAS);
+                    pr.seq0 = s->wave_seq;
+                    PCD_TRY(tiled_run_peer(D, W, H, 0, H, 0, spp, s->sweep_max + off + j, pr, s->sm_count, 0, s->stream));
+                    s->wave_seq += (unsigned)npass;
+                    cur ^= (npass & 1);
+                    j += npass * spp;
+                }
+                info->launches++;
             }
-            info->launches++;
+            PCD_CUDA(cudaEventRecord(s->ev_blk[b], s->stream));
+            PCD_CUDA(cudaStreamWaitEvent(s->aux_stream, s->ev_blk[b], 0));
+            PCD_CUDA(cudaMemcpyAsync(s->h_sweep_max + off, s->sweep_max + off, sizeof(unsigned long long) * k, cudaMemcpyDeviceToHost, s->aux_stream));
+            PCD_CUDA(cudaMemcpyAsync(s->h_flags + 2 + b, s->wave_ctl + WAVE_MAX_CTAS, sizeof(int), cudaMemcpyDeviceToHost, s->aux_stream));
+            PCD_CUDA(cudaEventRecord(s->ev_copied[b], s->aux_stream));
+            pend_k[b] = k; pend_first[b] = launched;
+            launched += k; ++blk; ++npend;
+            continue;
         }
-        PCD_CUDA(cudaEventRecord(s->evk1, s->stream));
-        PCD_CUDA(cudaMemcpyAsync(s->h_sweep_max, s->sweep_max, sizeof(unsigned long long) * k, cudaMemcpyDeviceToHost, s->stream));
-        if (!per_pass) PCD_CUDA(cudaMemcpyAsync(s->h_flags + 1, s->wave_ctl + WAVE_MAX_CTAS, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        PCD_CUDA(cudaStreamSynchronize(s->stream));
-        if (!per_pass && s->h_flags[1]) {
+        if (!npend) break;
+        const int b = head & 1, off = b * HALF, k = pend_k[b];
+        PCD_CUDA(cudaEventSynchronize(s->ev_copied[b]));
+        if (s->h_flags[2 + b]) {
             set_error("wavefront K-SOR kernel: a CTA gave up waiting for a neighbouring CTA");
             return PCD_ERR_CUDA;
         }
-        {
-            float kms = 0.f;
-            PCD_CUDA(cudaEventElapsedTime(&kms, s->evk0, s->evk1));
-            info->kernel_ms += kms;
-        }
-        for (int j = 0; j < k; ++j) {
+        for (int j = 0; j < k && !conv; ++j) {
             double m;
-            memcpy(&m, &s->h_sweep_max[j], sizeof(double));
-            if (!conv && m < tol) {
-                conv = done + j + 1;
-                last = m;
-            }
-            if (!conv && j == k - 1) last = m;
+            memcpy(&m, &s->h_sweep_max[off + j], sizeof(double));
+            if (m < tol) conv = pend_first[b] + j + 1;
+            if (conv || j == k - 1) last = m;
         }
-        done += k;
+        done = pend_first[b] + k;
+        ++head; --npend;
     }
+    PCD_CUDA(cudaEventRecord(s->evk1, s->stream));
     if (cur != 0) PCD_CUDA(cudaMemcpyAsync(phi, buf[cur], sizeof(double) * (size_t)W * H, cudaMemcpyDeviceToDevice, s->stream));
+    PCD_CUDA(cudaStreamSynchronize(s->stream));
+    {
+        float kms = 0.f;
+        PCD_CUDA(cudaEventElapsedTime(&kms, s->evk0, s->evk1));
+        info->kernel_ms += kms;
+    }
     info->sweeps = done;
     info->converged_at = conv;
     info->last_max_update = last;
@@ -235,7 +256,8 @@ int solver_init(pcd_solver *s, int W, int H, int device, int path, cudaStream_t 
     PCD_CUDA(cudaMalloc(&s->sweep_max, 2 * sizeof(unsigned long long) * (size_t)s->ring));  // per-sweep max + arrival slot
     PCD_CUDA(cudaMallocHost(&s->h_sweep_max, sizeof(unsigned long long) * 4096));
     PCD_CUDA(cudaMalloc(&s->d_flags, sizeof(int) * 4));
-    PCD_CUDA(cudaMallocHost(&s->h_flags, sizeof(int) * 4));
+    PCD_CUDA(cudaMallocHost(&s->h_flags, sizeof(int) * 8));
+    memset(s->h_flags, 0, sizeof(int) * 8);
     PCD_CUDA(cudaMalloc(&s->res_state, sizeof(ResState)));
     PCD_CUDA(cudaMallocHost(&s->h_res_state, sizeof(ResState)));
     PCD_CUDA(cudaEventCreate(&s->ev0));
@@ -264,6 +286,11 @@ void solver_free(pcd_solver *s) {
     cudaFree(s->sweep_max); cudaFreeHost(s->h_sweep_max);
     cudaFree(s->mask); cudaFree(s->d_flags); cudaFreeHost(s->h_flags);
     cudaFree(s->res_state); cudaFreeHost(s->h_res_state); cudaFree(s->halo); cudaFree(s->phi_alt); cudaFree(s->wave_ctl);
+    if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (s->ev_blk[i]) cudaEventDestroy(s->ev_blk[i]);
+        if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]);
+    }
     if (s->own_fields) { cudaFree(s->D); cudaFree(s->phi); }
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);

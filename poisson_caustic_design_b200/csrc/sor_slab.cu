@@ -9,6 +9,8 @@
 // The host layer (slab.py, torch.distributed: NCCL over NVLink, gloo in CPU tests) does the exchanges and
 // all-reduces the per-sweep max.  Per-cell arithmetic is the single-GPU kernels', so a G-slab solve is
 // bit-identical to the single-GPU solve (red-black updates of one colour are order-independent, max is exact).
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sor_common.cuh"
@@ -37,6 +39,8 @@ struct pcd_slab {
     unsigned *ctl = nullptr;              // see CTL_* above
     unsigned *done = nullptr;             // per-CTA sequence words of the persistent pass kernel [WAVE_MAX_CTAS]
     int passes_per_launch = 0;            // 0 = a whole block of sweeps per launch; 1 when a neighbour shares this device
+    unsigned long long *trace = nullptr;  // PCD_WAVE_TRACE=<prefix>: timestamps of the last launch, dumped at destroy
+    int trace_npass = 0;
     double *peer_phi[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [side][buffer], side 0 = up, 1 = down
     unsigned *peer_ctl[2] = {nullptr, nullptr};
     int peer_row0[2] = {0, 0};
@@ -157,6 +161,23 @@ int pcd_slab_create(int width, int height, int row0, int rows, int device, void 
 void pcd_slab_destroy(pcd_slab *s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    if (s->trace) {   // PCD_WAVE_TRACE=<prefix>: <prefix>_row<row0>.bin = int32 header [npass, max_ctas] + u64 [npass][max_ctas][4]
+        const char *prefix = getenv("PCD_WAVE_TRACE");
+        const size_t n = (size_t)4 * WAVE_MAX_CTAS * (s->trace_npass > 0 ? s->trace_npass : 1);
+        unsigned long long *h = (unsigned long long *)malloc(n * sizeof(unsigned long long));
+        if (prefix && h && cudaMemcpy(h, s->trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            char path[1200];
+            snprintf(path, sizeof(path), "%s_row%d.bin", prefix, s->row0);
+            if (FILE *f = fopen(path, "wb")) {
+                const int hdr[2] = {s->trace_npass, WAVE_MAX_CTAS};
+                fwrite(hdr, sizeof(int), 2, f);
+                fwrite(h, sizeof(unsigned long long), n, f);
+                fclose(f);
+            }
+        }
+        free(h);
+        cudaFree(s->trace);
+    }
     for (int side = 0; side < 2; ++side)
         if (s->peer_ipc[side]) {
             cudaIpcCloseMemHandle(s->peer_phi[side][0]);
@@ -172,6 +193,13 @@ int pcd_slab_device_ptrs(pcd_slab *s, void **phi0_dev, void **phi1_dev, void **s
     if (phi0_dev) *phi0_dev = s->phi[0];
     if (phi1_dev) *phi1_dev = s->phi[1];
     if (sweep_max_dev) *sweep_max_dev = s->sweep_max;
+    return PCD_OK;
+}
+
+// device address of the slab's error word (int; 1 = a pass ran into its time limit waiting for a neighbour)
+int pcd_slab_error_word(pcd_slab *s, void **err_dev) {
+    if (!s || !err_dev) { set_error("null argument"); return PCD_ERR_INVALID; }
+    *err_dev = s->ctl + CTL_ERR;
     return PCD_OK;
 }
 
@@ -395,6 +423,13 @@ int pcd_slab_peer_run(pcd_slab *s, int nsweeps, int slot) {
             pr.dn_buf[0] = s->peer_phi[1][0]; pr.dn_buf[1] = s->peer_phi[1][1]; pr.dn_grow0 = s->peer_row0[1] - s->GH;
             pr.wait_dn = s->ctl + CTL_FROM_DN; pr.sig_dn = s->peer_ctl[1] + CTL_FROM_UP;   // I am its upper neighbour
         }
+        static const char *trace_prefix = getenv("PCD_WAVE_TRACE");   // diagnostics: per-CTA, per-pass timestamps
+        if (trace_prefix && npass <= 64) {
+            if (!s->trace) PCD_CUDA(cudaMalloc(&s->trace, sizeof(unsigned long long) * 4 * WAVE_MAX_CTAS * 64));
+            PCD_CUDA(cudaMemsetAsync(s->trace, 0, sizeof(unsigned long long) * 4 * WAVE_MAX_CTAS * 64, s->stream));
+            pr.trace = s->trace;
+            s->trace_npass = npass;
+        }
         PCD_TRY(tiled_run_peer(s->D, s->W, s->H, s->row0, s->rows, s->row0 - s->GH, spp, s->sweep_max + slot + j, pr,
                                s->sm_count, s->sm_reserve, s->stream));
         s->seq += (unsigned)npass;
@@ -418,6 +453,12 @@ int pcd_slab_peer_error_to(pcd_slab *s, double *dst_dev) {
     if (!s || !dst_dev) { set_error("null argument"); return PCD_ERR_INVALID; }
     slab_error_to_kernel<<<1, 1, 0, s->stream>>>(s->ctl + CTL_ERR, dst_dev);
     PCD_LAUNCHED();
+    return PCD_OK;
+}
+
+int pcd_slab_clear_max_range(pcd_slab *s, int first, int n_slots) {
+    if (!s || first < 0 || n_slots < 0 || first + n_slots > s->ring) { set_error("bad slab / slot range"); return PCD_ERR_INVALID; }
+    PCD_CUDA(cudaMemsetAsync(s->sweep_max + first, 0, sizeof(unsigned long long) * n_slots, s->stream));
     return PCD_OK;
 }
 

@@ -104,6 +104,11 @@ __device__ __forceinline__ void seq_wait(const unsigned *flag, unsigned want, in
         __nanosleep(SYS ? 64 : 20);
     }
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // all threads of the CTA: the edge rows of this CTA's strip are stored in the neighbour's field; raise its flag there
 __device__ __forceinline__ void strip_signal(unsigned *flag, unsigned seq) {
     __syncthreads();
@@ -372,6 +377,11 @@ __global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __gr
             d.up_out = has_up ? p.peer.up_buf[oid] : nullptr;
             d.dn_out = has_dn ? p.peer.dn_buf[oid] : nullptr;
             d.slots = p.slots + (size_t)i * TS;
+            unsigned long long *tr = nullptr;
+            if (p.peer.trace && threadIdx.x == 0) {
+                tr = p.peer.trace + ((size_t)i * WAVE_MAX_CTAS + (by * nbx + bx)) * 4;
+                tr[0] = global_ns();
+            }
             // (1) dependencies of this pass.  Inside the GPU: the eight neighbouring CTAs have published pass seq-1 --
             // the only ones whose output this CTA reads and whose input it is about to overwrite (the launch boundary
             // covers the first pass).  Across GPUs: the neighbour's edge CTAs of strips bx-1..bx+1 have raised their
@@ -389,16 +399,23 @@ __global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __gr
                     const int nx = bx + tid - 65;
                     if (bot && nx >= 0 && nx < nbx) seq_wait<true>(p.peer.wait_dn + nx, seq - 1u, p.peer.err);
                 }
-                __syncthreads();
+                // a wait that ran into its limit (a neighbour died or never started) voids the whole launch: every CTA
+                // of this GPU leaves at its next pass boundary instead of spinning ~3 s per pass (the error word is
+                // per GPU; the neighbouring GPUs notice through their own waits)
+                const int dead = __syncthreads_or(threadIdx.x == 0 ? *((volatile int *)p.peer.err) : 0);
+                if (dead) break;
                 __threadfence();   // every thread's loads of this pass are ordered behind the flags observed above
             }
             // (2) the pass
+            if (tr) tr[1] = global_ns();
             if (!empty) wave_chunk<TS, true>(p, d, t, sphi, sD, wred, top, bot, seq);
             // (3) publish: every store of this CTA's pass is visible before its sequence word moves
             __syncthreads();
             if (threadIdx.x == 0) {
+                if (tr) tr[2] = global_ns();
                 __threadfence();
                 st_release_gpu(my_done, seq);
+                if (tr) tr[3] = global_ns();
             }
         }
     }

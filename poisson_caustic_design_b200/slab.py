@@ -146,11 +146,11 @@ class CudaSlabEngine:
     def store_device(self, phi_dev: int):
         _check(lib().pcd_slab_store_device(self._h, C.c_void_p(phi_dev)))
 
-    def clear_max(self, n: int):
-        _check(lib().pcd_slab_clear_max(self._h, n))
+    def clear_max(self, n: int, first: int = 0):
+        _check(lib().pcd_slab_clear_max_range(self._h, first, n))
 
-    def max_tensor(self, n: int):
-        return self._max[:n]
+    def max_tensor(self, n: int, first: int = 0):
+        return self._max[first:first + n]
 
     def download(self) -> np.ndarray:
         out = np.empty((self.rows, self.W), dtype=np.float64)
@@ -251,7 +251,9 @@ def solve(engine, dist, rank: int, world: int, max_iterations: int, tol: float, 
         engine.set_sm_reserve(8)   # room for the NCCL send/recv kernels next to the interior pass (this slab only)
     done, conv, last = 0, 0, 0.0
     try:
-        while done < max_iterations and not conv:
+        # same schedule as the fused path and the single-GPU large-grid solver: the stop is acted on ONE BLOCK LATE
+        while done < max_iterations:
+            was_conv = bool(conv)
             k = min(check_every, max_iterations - done)
             engine.clear_max(k)
             if wave and overlap:
@@ -287,8 +289,11 @@ def solve(engine, dist, rank: int, world: int, max_iterations: int, tol: float, 
             if world > 1:
                 dist.all_reduce(m, op=dist.ReduceOp.MAX)
             m_host = m.cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
-            conv, last = _decide(m_host, tol, done)
+            if not conv:
+                conv, last = _decide(m_host, tol, done)
             done += k
+            if was_conv:
+                break
     finally:
         if overlap:
             engine.set_sm_reserve(0)   # also when the loop raised: later solves on this slab get every SM back
@@ -296,29 +301,73 @@ def solve(engine, dist, rank: int, world: int, max_iterations: int, tol: float, 
 
 
 def _solve_peer(engine, dist, world: int, max_iterations: int, tol: float, check_every: int):
-    """Fused path: a block of check_every sweeps is nothing but back-to-back pass kernels (the ghost rows travel
-    inside them); the only collective is the all-reduce of the per-sweep maxima at the end of the block."""
+    """Fused path: a block of check_every sweeps is ONE persistent kernel launch (the ghost rows travel inside it); the
+    only collective is the all-reduce of the block's per-sweep maxima.  The stopping rule is evaluated ONE BLOCK LATE:
+    block b+1 is already queued when the maxima of block b reach the host (copied out on a side stream), so the GPUs
+    never drain between blocks; a solve that meets the rule in block b therefore executes block b+1 as well -- exactly
+    what the single-GPU large-grid solver does (run_tiled, csrc/sor_kernels.cu), so both end on the same bits."""
     import torch
-    check_every = max(1, min(check_every, 4095))
-    done, conv, last = 0, 0, 0.0
-    while done < max_iterations and not conv:
-        k = min(check_every, max_iterations - done)
-        engine.clear_max(k)
-        engine.peer_run(k, 0)
+    check_every = max(1, min(check_every, 2048))
+    half = 2048                                    # the slot ring holds two blocks: even blocks low half, odd high
+    launched, done, conv, last = 0, 0, 0, 0.0
+    side = getattr(engine, "_side_stream", None)
+    cuda = hasattr(engine, "_h")
+    if cuda and side is None:
+        side = engine._side_stream = torch.cuda.Stream()
+        engine._stage = [None, None]
+        engine._host = [torch.empty(half + 1, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+    pending = []                                   # blocks in flight: (k, first sweep, host getter)
+    blk = 0
+
+    def launch():
+        nonlocal launched, blk
+        k = min(check_every, max_iterations - launched)
+        off = (blk & 1) * half
+        engine.clear_max(k, off)
+        engine.peer_run(k, off)
         # the block's maxima plus, in the last slot, this rank's error word (a pass that waited ~3 s in vain for a
         # neighbour): one all-reduce (MAX) tells EVERY rank about a stalled neighbour in the same block, so all ranks
         # stop together instead of launching further passes on invalid ghost rows or blocking in a later collective
-        src = engine.max_tensor(k)
+        src = engine.max_tensor(k, off)
         m = torch.empty(k + 1, dtype=src.dtype, device=src.device)
         m[:k].copy_(src)
         engine.peer_error_into(m[k:])
         dist.all_reduce(m, op=dist.ReduceOp.MAX)
-        m_host = m.cpu().numpy()
+        if cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            host = engine._host[blk & 1]
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                host[:k + 1].copy_(m, non_blocking=True)
+                got = torch.cuda.Event()
+                got.record(side)
+            m.record_stream(side)
+
+            def fetch(host=host, got=got, k=k):
+                got.synchronize()
+                return host[:k + 1].numpy().copy()
+        else:
+            def fetch(m=m):
+                return m.numpy().copy()
+        pending.append((k, launched, fetch))
+        launched += k
+        blk += 1
+
+    while True:
+        if launched < max_iterations and not conv and len(pending) < 2:
+            launch()
+            continue
+        if not pending:
+            break
+        k, first, fetch = pending.pop(0)
+        m_host = fetch()
         if m_host[k] != 0.0:
             raise RuntimeError("slab solve: a pass gave up waiting for a neighbouring rank's ghost rows "
-                               f"(reported by at least one rank in sweeps {done + 1}..{done + k}; every rank stops here)")
-        conv, last = _decide(m_host[:k], tol, done)
-        done += k
+                               f"(reported by at least one rank in sweeps {first + 1}..{first + k}; every rank stops here)")
+        done = first + k
+        if not conv:
+            conv, last = _decide(m_host[:k], tol, first)
     return {"sweeps": done, "converged_at": conv, "last_max_update": last, "mode": "peer"}
 
 
@@ -334,7 +383,8 @@ def solve_local_peer(engines, max_iterations: int, tol: float, check_every: int 
         engines[0]._local_connected = True
     check_every = max(1, min(check_every, 4096))
     done, conv, last = 0, 0, 0.0
-    while done < max_iterations and not conv:
+    while done < max_iterations:          # the stop is acted on one block late (see _solve_peer)
+        was_conv = bool(conv)
         k = min(check_every, max_iterations - done)
         for e in engines:
             e.clear_max(k)
@@ -344,8 +394,11 @@ def solve_local_peer(engines, max_iterations: int, tol: float, check_every: int 
         m = engines[0].max_tensor(k).clone()
         for e in engines[1:]:
             m = torch.maximum(m, e.max_tensor(k))
-        conv, last = _decide(m.cpu().numpy(), tol, done)
+        if not conv:
+            conv, last = _decide(m.cpu().numpy(), tol, done)
         done += k
+        if was_conv:
+            break
     if any(e.peer_timed_out() for e in engines):
         raise RuntimeError("slab solve: a pass gave up waiting for a neighbouring slab's ghost rows")
     return {"sweeps": done, "converged_at": conv, "last_max_update": last, "mode": "peer"}
@@ -372,7 +425,8 @@ def solve_local(engines, max_iterations: int, tol: float, check_every: int = 64,
             up.phi[GH + up.rows:GH + up.rows + depth].copy_(dn.phi[GH:GH + depth])
 
     done, conv, last = 0, 0, 0.0
-    while done < max_iterations and not conv:
+    while done < max_iterations:          # the stop is acted on one block late (see _solve_peer)
+        was_conv = bool(conv)
         k = min(check_every, max_iterations - done)
         for e in engines:
             e.clear_max(k)
@@ -400,8 +454,11 @@ def solve_local(engines, max_iterations: int, tol: float, check_every: int = 64,
         m = engines[0].max_tensor(k).clone()
         for e in engines[1:]:
             m = torch.maximum(m, e.max_tensor(k).to(m.device))
-        conv, last = _decide(m.cpu().numpy(), tol, done)
+        if not conv:
+            conv, last = _decide(m.cpu().numpy(), tol, done)
         done += k
+        if was_conv:
+            break
     return {"sweeps": done, "converged_at": conv, "last_max_update": last, "mode": "wavefront" if wave else "colour"}
 
 

@@ -74,11 +74,11 @@ class NumpySlabEngine:
             for colour in (0, 1):
                 self._update(colour, slot + t, 1, self.LR - 1)
 
-    def clear_max(self, n):
-        self._max[:n] = 0.0
+    def clear_max(self, n, first=0):
+        self._max[first:first + n] = 0.0
 
-    def max_tensor(self, n):
-        return self._max[:n]
+    def max_tensor(self, n, first=0):
+        return self._max[first:first + n]
 
     def download(self):
         return self.phi.numpy()[self.GH:self.GH + self.rows].copy()

@@ -57,7 +57,7 @@ def test_convergence_rule_and_lag(pcd, port, golden, path):
         _, n_exact, conv_exact, _ = port.poisson_rb(D, z, 100000, 1e-7)
         assert info["converged_at"] == conv_exact == n_exact           # same sweep satisfies the test
         extra = info["sweeps"] - info["converged_at"]
-        assert 0 <= extra <= 64
+        assert 0 <= extra <= 128        # large-grid path: blocks of 64 sweeps, the stop is acted on one block late
         want, n, conv, _ = port.poisson_rb(D, z, 100000, 1e-7, extra_sweeps=extra)
         assert n == info["sweeps"] and np.array_equal(got, want)
         assert info["last_max_update"] < 1e-7

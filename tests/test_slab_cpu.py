@@ -99,7 +99,7 @@ def test_gloo_slabs_stopping_rule(port, tmp_path):
     phi, info = run_world(2, D, z, 100000, 1e-7, 16, tmp_path, 29650)
     _, n_exact, conv_exact, _ = port.poisson_rb(D, z, 100000, 1e-7)
     assert int(info[1]) == conv_exact                 # same sweep satisfies max|delta| < tol
-    assert int(info[0]) % 16 == 0 and 0 <= int(info[0]) - conv_exact < 16
+    assert int(info[0]) % 16 == 0 and 16 <= int(info[0]) - conv_exact < 32    # the stop is acted on one block late
     want = port.poisson_rb(D, z, 100000, 1e-7, extra_sweeps=int(info[0]) - conv_exact)[0]
     assert np.array_equal(phi, want)
     assert info[2] < 1e-7
@@ -186,4 +186,4 @@ def test_gloo_peer_mode_stalled_neighbour_stops_every_rank_together(tmp_path):
     mp.spawn(_stall_worker, args=(world, 29691, D, np.zeros_like(D), str(tmp_path), 1), nprocs=world, join=True)
     res = [np.load(tmp_path / f"stall_{r}.npy") for r in range(world)]
     for r in res:
-        assert r[0] == 1 and r[1] == 2 and r[2] == 2      # all raised, all after the second block
+        assert r[0] == 1 and r[1] == 3 and r[2] == 3      # all raised together: block 3 was already queued when block 2's word arrived

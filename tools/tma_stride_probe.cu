@@ -1,0 +1,141 @@
+// Probe (round 2): can TMA de-interleave a row of doubles by column parity?  A 2-D tensor map over a row-major W x H
+// fp64 array with elementStrides = {2, 1} and a box of {256, 1} (box extents are limited to 256) should deliver every
+// second element of a 256-column window -- 128 doubles, dense in shared memory -- and zero-fill whatever lies outside the
+// array.  Four such loads per row (window halves x origin even / odd) give the column-parity split the wavefront K-SOR
+// kernel wants, with the global layout left as it is.  Checks values + OOB fill, then times a streaming loop against 8-byte cp.async.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/tma_stride_probe tools/tma_stride_probe.cu
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                             const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, int n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(n)); }
+__device__ __forceinline__ void mbar_expect(unsigned long long *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE;\nbra WAIT;\nDONE:\n}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *b) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(b)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__global__ void check_kernel(const __grid_constant__ CUtensorMap map, double *out, int x0, int y) {
+    __shared__ __align__(128) double buf[2][256];
+    __shared__ unsigned long long bar;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect(&bar, 4 * 1024);
+        tma_load_2d(&buf[0][0], &map, x0, y, &bar);
+        tma_load_2d(&buf[0][128], &map, x0 + 256, y, &bar);
+        tma_load_2d(&buf[1][0], &map, x0 + 1, y, &bar);
+        tma_load_2d(&buf[1][128], &map, x0 + 257, y, &bar);
+    }
+    mbar_wait(&bar, 0);
+    out[threadIdx.x] = buf[0][threadIdx.x];
+    out[256 + threadIdx.x] = buf[1][threadIdx.x];
+}
+
+// streaming: every CTA walks `rows` rows of its 512-column window, PF rows ahead, and sums what it gets
+template <bool TMA>
+__global__ void __launch_bounds__(256, 2) stream_kernel(const __grid_constant__ CUtensorMap map, const double *src, int W, int rows_per_cta, double *sink) {
+    constexpr int R = 4;
+    __shared__ __align__(128) double buf[R][2][256];
+    __shared__ unsigned long long bar[R];
+    const int k = threadIdx.x, x0 = blockIdx.x * 512, r0 = blockIdx.y * rows_per_cta;
+    if (TMA && k == 0) { for (int i = 0; i < R; ++i) mbar_init(&bar[i], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    double acc = 0.0;
+    auto issue = [&](int r) {
+        const int sl = r % R;
+        if (TMA) {
+            if (k == 0) {
+                mbar_expect(&bar[sl], 4 * 1024);
+                tma_load_2d(&buf[sl][0][0], &map, x0, r0 + r, &bar[sl]);
+                tma_load_2d(&buf[sl][0][128], &map, x0 + 256, r0 + r, &bar[sl]);
+                tma_load_2d(&buf[sl][1][0], &map, x0 + 1, r0 + r, &bar[sl]);
+                tma_load_2d(&buf[sl][1][128], &map, x0 + 257, r0 + r, &bar[sl]);
+            }
+        } else {
+            const double *g = src + (size_t)(r0 + r) * W + x0 + 2 * k;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&buf[sl][0][k])), "l"(g));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&buf[sl][1][k])), "l"(g + 1));
+            asm volatile("cp.async.commit_group;");
+        }
+    };
+    for (int r = 0; r < R - 1; ++r) issue(r);
+    for (int r = 0; r < rows_per_cta; ++r) {
+        if (r + R - 1 < rows_per_cta) issue(r + R - 1);
+        else if (!TMA) asm volatile("cp.async.commit_group;");
+        const int sl = r % R;
+        if (TMA) mbar_wait(&bar[sl], (r / R) & 1);
+        else asm volatile("cp.async.wait_group %0;" ::"n"(R - 1));
+        __syncthreads();
+        acc += buf[sl][0][k] + buf[sl][1][(k + 1) & 255];
+        __syncthreads();
+    }
+    if (acc == 12345.678) sink[0] = acc;
+}
+
+int main() {
+    const int W = 8192, H = 4096;
+    std::vector<double> h((size_t)W * H);
+    for (size_t i = 0; i < h.size(); ++i) h[i] = (double)(i % 1000003) + 0.5;
+    double *d, *out, *sink;
+    cudaMalloc(&d, h.size() * 8); cudaMalloc(&out, 512 * 8); cudaMalloc(&sink, 8);
+    cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
+    EncodeFn enc = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&enc, cudaEnableDefault, &q) != cudaSuccess || !enc) { printf("no cuTensorMapEncodeTiled\n"); return 1; }
+    CUtensorMap map;
+    cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H}, strides[1] = {(cuuint64_t)W * 8};
+    cuuint32_t box[2] = {256, 1}, estr[2] = {2, 1};
+    CUresult rc = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    printf("encode rc=%d\n", (int)rc);
+    if (rc != CUDA_SUCCESS) return 1;
+    int bad = 0;
+    const int cases[][2] = {{0, 0}, {504, 7}, {-4, 3}, {W - 100, H - 1}, {1000, -1}, {1000, H}};
+    for (auto &c : cases) {
+        check_kernel<<<1, 256>>>(map, out, c[0], c[1]);
+        std::vector<double> o(512);
+        cudaError_t e = cudaMemcpy(o.data(), out, 512 * 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { printf("cuda error %s\n", cudaGetErrorString(e)); return 1; }
+        for (int p = 0; p < 2; ++p)
+            for (int k = 0; k < 256; ++k) {
+                const int x = c[0] + p + 2 * k, y = c[1];
+                const double want = (x >= 0 && x < W && y >= 0 && y < H) ? h[(size_t)y * W + x] : 0.0;
+                if (o[p * 256 + k] != want) { if (bad < 5) printf("mismatch case (%d,%d) p=%d k=%d got %g want %g\n", c[0], c[1], p, k, o[p * 256 + k], want); ++bad; }
+            }
+    }
+    printf("values: %s (%d mismatches)\n", bad ? "WRONG" : "ok", bad);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int tma = 0; tma < 2; ++tma) {
+        const dim3 grid(W / 512, 18);   // 288 CTAs, 2 per SM
+        const int rows = H / 18;
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(e0);
+            if (tma) stream_kernel<true><<<grid, 256>>>(map, d, W, rows, sink);
+            else stream_kernel<false><<<grid, 256>>>(map, d, W, rows, sink);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep == 2) printf("%s: %.3f ms for %d rows x %d cols = %.1f GB/s, %.3f us per row step\n", tma ? "TMA stride-2 x4" : "cp.async 8B x2", ms,
+                                 rows * 18, W, (double)rows * 18 * W * 8 / ms / 1e6, ms * 1e3 / rows);
+        }
+    }
+    printf("last error: %s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
