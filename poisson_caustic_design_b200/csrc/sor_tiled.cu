@@ -127,25 +127,49 @@ struct WaveThread {  // per-thread invariants
 
 // One row step.  C = (f - ys) mod R is compile-time; chunks start so that the active cell of row r in phase ph
 // has window parity (r - ys + 1 + ph) & 1, i.e. (C + ph) & 1 for the row f-1-2ph updated at offset C.
-template <int TS, int C, bool STEADY, bool PEER>
+// MODE (per block of R steps, CTA-uniform):
+//   WAVE_STEADY   every row any phase touches is owned by the chunk and no domain edge is near: no checks at all;
+//   WAVE_CHECKED  a block at the top / bottom of a chunk.  Rows outside the dependency pyramid of the owned rows are
+//                 simply updated as well -- their (stale) values are never read by a row inside the pyramid of a later
+//                 phase, so they cannot reach an owned value -- and only what leaves the CTA is guarded: the per-sweep
+//                 maximum and the store to the output field (owned rows only), the rows streamed in (they must exist).
+//                 Rows outside the grid stay 0.0 (a missing neighbour reads 0.0) and the domain's first / last row use
+//                 their own neighbour count.
+constexpr int WAVE_STEADY = 0, WAVE_CHECKED = 1;
+
+template <int TS, int C, int MODE>
 __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveDyn &d, const WaveThread &t, const int f,
                                           double (&v)[WaveCfg<TS>::R][2], double *__restrict__ sphi,
                                           double *__restrict__ sD, double (&lmax)[TS]) {
     using Cfg = WaveCfg<TS>;
     constexpr int R = Cfg::R, NP = Cfg::NP, PITCH = Cfg::PITCH;
     const int W = p.W, H = p.H, k = t.k;
-    // (a) stream row f+PF into ring slot (C+PF)%R: 8-byte cp.async per cell, zero-filled outside the grid
+    // (a) stream row f+PF into ring slot (C+PF)%R, 8-byte cp.async per cell.  Columns outside the grid are never copied
+    // and never updated in STEADY blocks: their slots keep the 0.0 the ring was initialised with; CHECKED blocks zero-fill
+    // rows that lie outside the grid or behind the chunk's last needed row.
     {
         constexpr int SL = (C + WAVE_PF) % R;
         const int fr = f + WAVE_PF;
-        const bool row_ok = STEADY ? true : (fr <= t.ye && fr >= 0 && fr < H);
-        const size_t base = row_ok ? (size_t)(fr - p.grow0) * W : 0;
-        const bool a0 = row_ok && t.ex0, a1 = row_ok && t.ex1;
-        const size_t o0 = a0 ? base + t.gx0 : 0, o1 = a1 ? base + t.gx0 + 1 : 0;
-        __pipeline_memcpy_async(sphi + (SL * 2 + 0) * PITCH + 1 + k, d.phi_in + o0, 8, a0 ? 0 : 8);
-        __pipeline_memcpy_async(sphi + (SL * 2 + 1) * PITCH + 1 + k, d.phi_in + o1, 8, a1 ? 0 : 8);
-        __pipeline_memcpy_async(sD + (SL * 2 + 0) * PITCH + 1 + k, p.D + o0, 8, a0 ? 0 : 8);
-        __pipeline_memcpy_async(sD + (SL * 2 + 1) * PITCH + 1 + k, p.D + o1, 8, a1 ? 0 : 8);
+        if constexpr (MODE == WAVE_CHECKED) {
+            const bool row_ok = fr <= t.ye && fr >= 0 && fr < H;
+            const size_t base = row_ok ? (size_t)(fr - p.grow0) * W : 0;
+            const bool a0 = row_ok && t.ex0, a1 = row_ok && t.ex1;
+            const size_t o0 = a0 ? base + t.gx0 : 0, o1 = a1 ? base + t.gx0 + 1 : 0;
+            __pipeline_memcpy_async(sphi + (SL * 2 + 0) * PITCH + 1 + k, d.phi_in + o0, 8, a0 ? 0 : 8);
+            __pipeline_memcpy_async(sphi + (SL * 2 + 1) * PITCH + 1 + k, d.phi_in + o1, 8, a1 ? 0 : 8);
+            __pipeline_memcpy_async(sD + (SL * 2 + 0) * PITCH + 1 + k, p.D + o0, 8, a0 ? 0 : 8);
+            __pipeline_memcpy_async(sD + (SL * 2 + 1) * PITCH + 1 + k, p.D + o1, 8, a1 ? 0 : 8);
+        } else {
+            const size_t o = (size_t)(fr - p.grow0) * W + t.gx0;
+            if (t.ex0) {
+                __pipeline_memcpy_async(sphi + (SL * 2 + 0) * PITCH + 1 + k, d.phi_in + o, 8);
+                __pipeline_memcpy_async(sD + (SL * 2 + 0) * PITCH + 1 + k, p.D + o, 8);
+            }
+            if (t.ex1) {
+                __pipeline_memcpy_async(sphi + (SL * 2 + 1) * PITCH + 1 + k, d.phi_in + o + 1, 8);
+                __pipeline_memcpy_async(sD + (SL * 2 + 1) * PITCH + 1 + k, p.D + o + 1, 8);
+            }
+        }
         __pipeline_commit();
     }
     // (b) row f becomes active: own pair from the smem ring into the register ring
@@ -162,9 +186,8 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveDyn &d,
         const int SL = (C - 1 - 2 * ph + 2 * R) % R;
         const int q = (C + ph) & 1;  // compile-time after unrolling
         const int r = f - 1 - 2 * ph;
-        // rows that still matter for the owned rows: the dependency pyramid shrinks by one row per phase
-        bool a = q ? t.ex1 : t.ex0;
-        if (!STEADY) a = a && !(r < t.y0 - (NP - 1 - ph) || r > t.y1 - 1 + (NP - 1 - ph) || r < 0 || r >= H);
+        bool a = q ? t.ex1 : t.ex0;                           // columns outside the grid stay 0.0
+        if (MODE == WAVE_CHECKED) a = a && r >= 0 && r < H;   // ... and so do rows outside the grid
         act[ph] = a;
         nbv[ph] = q ? sphi[(SL * 2 + 0) * PITCH + 1 + k + 1] : sphi[(SL * 2 + 1) * PITCH + 1 + k - 1];
         Dvv[ph] = sD[(SL * 2 + q) * PITCH + 1 + k];
@@ -180,7 +203,7 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveDyn &d,
         const double val = v[SL][q];
         const double sum = ((l + u) + rr) + dn;  // ghost rows / columns read 0.0: identical to skipping them
         double delta;
-        if (!STEADY && (r == 0 || r == H - 1)) {  // CTA-uniform: domain top / bottom row
+        if (MODE == WAVE_CHECKED && (r == 0 || r == H - 1)) {  // CTA-uniform: domain top / bottom row (two rows of the grid)
             const int cnt = (int)t.cx[q] - (r == 0 ? 1 : 0) - (r == H - 1 ? 1 : 0);
             delta = wsel(p.w, cnt) * ((sum - (double)cnt * val) - Dvv[ph]);
         } else {
@@ -189,7 +212,7 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveDyn &d,
         const double nv = act[ph] ? val + delta : val;
         nvv[ph] = nv;
         v[SL][q] = nv;
-        if (act[ph] && t.core && (STEADY || (r >= t.y0 && r < t.y1))) {
+        if (act[ph] && t.core && (MODE == WAVE_STEADY || (r >= t.y0 && r < t.y1))) {
             const double ad = fabs(delta);
             if (ad > lmax[ph / 2]) lmax[ph / 2] = ad;
         }
@@ -204,22 +227,13 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveDyn &d,
     {
         constexpr int SL = (C - 1 - 2 * (NP - 1) + 2 * R) % R;
         const int r = f - 1 - 2 * (NP - 1);
-        if (t.core && (STEADY || (r >= t.y0 && r < t.y1))) {
+        if (t.core && (MODE == WAVE_STEADY || (r >= t.y0 && r < t.y1))) {
             const size_t o = (size_t)(r - p.grow0) * W + t.gx0;
             if (t.ex0 && t.ex1 && ((W & 1) == 0)) {
                 *reinterpret_cast<double2 *>(d.phi_out + o) = make_double2(v[SL][0], v[SL][1]);
             } else {
                 if (t.ex0) d.phi_out[o] = v[SL][0];
                 if (t.ex1) d.phi_out[o + 1] = v[SL][1];
-            }
-            if constexpr (PEER && !STEADY) {  // rows next to a slab edge also go to the neighbour's ghost rows
-                double *dst = nullptr;
-                if (d.up_out && r < p.row_first + p.peer.gh) dst = d.up_out + (size_t)(r - p.peer.up_grow0) * W + t.gx0;
-                if (d.dn_out && r >= p.row_first + p.rows - p.peer.gh) dst = d.dn_out + (size_t)(r - p.peer.dn_grow0) * W + t.gx0;
-                if (dst) {
-                    if (t.ex0) dst[0] = v[SL][0];
-                    if (t.ex1) dst[1] = v[SL][1];
-                }
             }
         }
     }
@@ -228,16 +242,34 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveDyn &d,
     __syncthreads();
 }
 
-template <int TS, int C, bool STEADY, bool PEER>
+template <int TS, int C, int MODE>
 struct WaveUnroll {
     static __device__ __forceinline__ void run(const WaveParams &p, const WaveDyn &d, const WaveThread &t, const int f,
                                                const int f_last, double (&v)[WaveCfg<TS>::R][2], double *sphi, double *sD,
                                                double (&lmax)[TS]) {
-        if (!STEADY && f + C > f_last) return;  // CTA-uniform: the chunk's last block stops at its last step
-        wave_step<TS, C, STEADY, PEER>(p, d, t, f + C, v, sphi, sD, lmax);
-        if constexpr (C + 1 < WaveCfg<TS>::R) WaveUnroll<TS, C + 1, STEADY, PEER>::run(p, d, t, f, f_last, v, sphi, sD, lmax);
+        if (MODE != WAVE_STEADY && f + C > f_last) return;  // CTA-uniform: the chunk's last block stops at its last step
+        wave_step<TS, C, MODE>(p, d, t, f + C, v, sphi, sD, lmax);
+        if constexpr (C + 1 < WaveCfg<TS>::R) WaveUnroll<TS, C + 1, MODE>::run(p, d, t, f, f_last, v, sphi, sD, lmax);
     }
 };
+
+// Ghost rows of a neighbouring slab: every thread copies ITS OWN two columns of `nrows` finished rows of this pass's
+// output field (it stored them itself a few steps ago) into the neighbour's output field -- plain stores to peer memory
+// over NVLink.  Kept out of the row step so that the hot loop carries neither the code nor the registers for it.
+__device__ __forceinline__ void push_rows(const WaveParams &p, const WaveDyn &d, const WaveThread &t, double *dst_base,
+                                          const int dst_grow0, const int first_row, const int nrows) {
+    if (!t.core || !(t.ex0 || t.ex1)) return;
+    for (int r = first_row; r < first_row + nrows; ++r) {
+        const double *src = d.phi_out + (size_t)(r - p.grow0) * p.W + t.gx0;
+        double *dst = dst_base + (size_t)(r - dst_grow0) * p.W + t.gx0;
+        if (t.ex0 && t.ex1 && ((p.W & 1) == 0)) {
+            *reinterpret_cast<double2 *>(dst) = __ldcg(reinterpret_cast<const double2 *>(src));
+        } else {
+            if (t.ex0) dst[0] = __ldcg(src);
+            if (t.ex1) dst[1] = __ldcg(src + 1);
+        }
+    }
+}
 
 // One pass of one CTA over its chunk.  top / bot: this chunk touches the slab's first / last owned rows AND a
 // neighbouring slab is attached there (its ghost rows are fed from here, flag value `seq`).
@@ -272,28 +304,35 @@ __device__ __forceinline__ void wave_chunk(const WaveParams &p, const WaveDyn &d
     __syncthreads();
 
     const int f_last = t.y1 + 2 * (NP - 1);
-    bool up_sent = false;
+    bool up_sent = false, up_pushed = false;
     for (int fb = t.ys; fb <= f_last; fb += R) {
         // a block of R steps is steady when every row any phase touches is owned and not a domain edge row, and
         // every row streamed in exists
         const int r_min = fb - 1 - 2 * (NP - 1), r_max = fb + R - 2, f_max = fb + R - 1 + WAVE_PF;
-        bool steady = r_min >= max(t.y0, 1) && r_max <= min(t.y1 - 1, H - 2) && f_max <= min(t.ye, H - 1);
-        if constexpr (PEER) {  // rows stored by this block: r_min .. r_min + R - 1; edge rows take the checked variant
-            if (top && r_min < p.row_first + p.peer.gh) steady = false;
-            if (bot && r_min + R - 1 >= p.row_first + p.rows - p.peer.gh) steady = false;
-        }
-        if (steady) WaveUnroll<TS, 0, true, PEER>::run(p, d, t, fb, f_last, v, sphi, sD, lmax);
-        else WaveUnroll<TS, 0, false, PEER>::run(p, d, t, fb, f_last, v, sphi, sD, lmax);
-        if constexpr (PEER) {  // the top edge rows are complete long before the chunk is: tell the upper neighbour now
-            if (top && !up_sent && r_min + R - 1 >= p.row_first + p.peer.gh - 1) {
+        const bool steady = r_min >= max(t.y0, 1) && r_max <= min(t.y1 - 1, H - 2) && f_max <= min(t.ye, H - 1);
+        if (steady) WaveUnroll<TS, 0, WAVE_STEADY>::run(p, d, t, fb, f_last, v, sphi, sD, lmax);
+        else WaveUnroll<TS, 0, WAVE_CHECKED>::run(p, d, t, fb, f_last, v, sphi, sD, lmax);
+        if constexpr (PEER) {
+            // The top edge rows are complete long before the chunk is: copy them into the upper neighbour's ghost rows
+            // now, and raise its flag ONE BLOCK LATER, when the peer stores have long been acknowledged -- the
+            // system-scope fence in front of the flag then costs nothing (this CTA is the critical one of the pass).
+            if (top && up_pushed && !up_sent) {
                 strip_signal(p.peer.sig_up + blockIdx.x, seq);
                 up_sent = true;
+            }
+            if (top && !up_pushed && r_min + R - 1 >= p.row_first + p.peer.gh - 1) {
+                push_rows(p, d, t, d.up_out, p.peer.up_grow0, p.row_first, p.peer.gh);
+                up_pushed = true;
             }
         }
     }
     if constexpr (PEER) {
+        if (top && !up_pushed) push_rows(p, d, t, d.up_out, p.peer.up_grow0, p.row_first, p.peer.gh);
         if (top && !up_sent) strip_signal(p.peer.sig_up + blockIdx.x, seq);
-        if (bot) strip_signal(p.peer.sig_dn + blockIdx.x, seq);
+        if (bot) {
+            push_rows(p, d, t, d.dn_out, p.peer.dn_grow0, p.row_first + p.rows - p.peer.gh, p.peer.gh);
+            strip_signal(p.peer.sig_dn + blockIdx.x, seq);
+        }
     }
 
     // publish the per-sweep maxima

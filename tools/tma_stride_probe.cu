@@ -46,6 +46,19 @@ __global__ void check_kernel(const __grid_constant__ CUtensorMap map, double *ou
     out[256 + threadIdx.x] = buf[1][threadIdx.x];
 }
 
+__global__ void check_plain_kernel(const __grid_constant__ CUtensorMap map, double *out, int x0, int y) {
+    __shared__ __align__(128) double buf[256];
+    __shared__ unsigned long long bar;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect(&bar, 2048);
+        tma_load_2d(buf, &map, x0, y, &bar);
+    }
+    mbar_wait(&bar, 0);
+    out[threadIdx.x] = buf[threadIdx.x];
+}
+
 // streaming: every CTA walks `rows` rows of its 512-column window, PF rows ahead, and sums what it gets
 template <bool TMA>
 __global__ void __launch_bounds__(256, 2) stream_kernel(const __grid_constant__ CUtensorMap map, const double *src, int W, int rows_per_cta, double *sink) {
@@ -104,6 +117,19 @@ int main() {
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     printf("encode rc=%d\n", (int)rc);
     if (rc != CUDA_SUCCESS) return 1;
+    {   // scaffolding check: the same PTX with an ordinary (stride 1) map
+        CUtensorMap pm;
+        cuuint32_t pbox[2] = {256, 1}, pstr[2] = {1, 1};
+        CUresult prc = enc(&pm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d, dims, strides, pbox, pstr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        check_plain_kernel<<<1, 256>>>(pm, out, 504, 7);
+        std::vector<double> o(256);
+        cudaError_t e = cudaMemcpy(o.data(), out, 256 * 8, cudaMemcpyDeviceToHost);
+        int pb = 0;
+        for (int k = 0; k < 256; ++k) pb += o[k] != h[(size_t)7 * W + 504 + k];
+        printf("plain map: encode rc=%d, %s, %d mismatches\n", (int)prc, cudaGetErrorString(e), pb);
+        if (e != cudaSuccess) return 1;
+    }
     int bad = 0;
     const int cases[][2] = {{0, 0}, {504, 7}, {-4, 3}, {W - 100, H - 1}, {1000, -1}, {1000, H}};
     for (auto &c : cases) {

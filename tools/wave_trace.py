@@ -42,7 +42,7 @@ def summarise(t):
 
 
 if __name__ == "__main__":
-    paths = [a for a in sys.argv[1:] if not a.startswith("--")]
+    paths = [a for a in sys.argv[1:] if a.endswith(".bin")]
     out = {}
     for p in sorted(paths):
         out[p.split("/")[-1]] = summarise(load(p))
