@@ -74,6 +74,8 @@ struct pcd_solver {
     double *phi_alt = nullptr;      // device: ping-pong partner of phi on the tiled path
     unsigned *wave_ctl = nullptr;   // device: per-CTA sequence words + error word of the persistent wavefront kernel
     unsigned wave_seq = 0;          // sequence number of the last pass it executed
+    unsigned long long *wave_trace = nullptr;   // PCD_WAVE_TRACE diagnostics (timestamps of the last launch)
+    int wave_trace_npass = 0;
     cudaStream_t aux_stream = nullptr;                         // copies a block's maxima out while the next block runs
     cudaEvent_t ev_blk[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     void *dct_state = nullptr;      // opt-in direct backend (dct_solver.cu): DCT matrices, eigenvalues, temporaries

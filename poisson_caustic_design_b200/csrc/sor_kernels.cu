@@ -8,15 +8,18 @@
 // -fmad=false, so the field after n sweeps is bit-identical to the red-black restatement
 // kept under oracle/ (test infrastructure; nothing here includes or links it).
 //
-// Two kernel families:
-//   * streaming : one launch per colour, phi/D streamed through L2/HBM; any grid size.
-//   * resident  : ONE persistent cooperative kernel per solve.  Each CTA (one per SM) owns a slab of
-//                 rows; phi lives in shared memory (column-parity split, conflict-free), D / phi /
-//                 neighbour masks of the thread's own cells live in registers; slab boundary rows are
-//                 exchanged between neighbouring CTAs through L2 with flag-in-data ("LL") 16-byte
-//                 messages, so there is no grid-wide barrier and no fence on the critical path; the
-//                 convergence test is a per-sweep atomicMax + arrival counter evaluated with a fixed
-//                 lag by a dedicated control warp.
+// Three kernel families behind one entry point (solver_run), all producing the same bits:
+//   * streaming (this file): one launch per colour, phi/D streamed through L2/HBM; any grid size; with per-cell
+//                 neighbour masks it is also the path for D with NaN holes.
+//   * resident  (sor_resident.cu): ONE persistent kernel per solve for grids up to ~1024^2.  Each CTA (one per SM,
+//                 launched as clusters of two) owns a slab of rows; phi AND D of a thread's column pair live in
+//                 registers for the whole solve, only the left/right neighbour goes through shared memory; slab boundary
+//                 rows travel as 16-byte flag-in-data messages through L2 (DSMEM inside a pair), polled by the consuming
+//                 thread; no grid-wide and no CTA-wide barrier in the sweep loop; per-sweep verdicts are published with one
+//                 atomic per CTA and acted on with a fixed lag.
+//   * wavefront (sor_tiled.cu): temporal blocking for larger grids and multi-GPU slabs, one persistent launch per block of
+//                 sweeps between two convergence tests.
+// plus the opt-in direct backend (dct_solver.cu).
 #include <cstdlib>
 #include <cstring>
 
@@ -186,6 +189,13 @@ static int run_tiled(pcd_solver *s, const double *D, double *phi, int max_it, do
                     pr.done = s->wave_ctl;
                     pr.err = reinterpret_cast<int *>(s->wave_ctl + WAVE_MAX_CTAS);
                     pr.seq0 = s->wave_seq;
+                    static const char *trace_prefix = getenv("PCD_WAVE_TRACE");   // diagnostics: per-CTA, per-pass timestamps
+                    if (trace_prefix && npass <= 64) {
+                        if (!s->wave_trace) PCD_CUDA(cudaMalloc(&s->wave_trace, sizeof(unsigned long long) * 4 * WAVE_MAX_CTAS * 64));
+                        PCD_CUDA(cudaMemsetAsync(s->wave_trace, 0, sizeof(unsigned long long) * 4 * WAVE_MAX_CTAS * 64, s->stream));
+                        pr.trace = s->wave_trace;
+                        s->wave_trace_npass = npass;
+                    }
                     PCD_TRY(tiled_run_peer(D, W, H, 0, H, 0, spp, s->sweep_max + off + j, pr, s->sm_count, 0, s->stream));
                     s->wave_seq += (unsigned)npass;
                     cur ^= (npass & 1);
@@ -282,6 +292,23 @@ int solver_init(pcd_solver *s, int W, int H, int device, int path, cudaStream_t 
 
 void solver_free(pcd_solver *s) {
     if (!s) return;
+    if (s->wave_trace) {   // PCD_WAVE_TRACE=<prefix>: <prefix>_solver<W>x<H>.bin, same format as the slabs' dumps (tools/wave_trace.py)
+        const char *prefix = getenv("PCD_WAVE_TRACE");
+        const size_t n = (size_t)4 * WAVE_MAX_CTAS * (s->wave_trace_npass > 0 ? s->wave_trace_npass : 1);
+        unsigned long long *h = (unsigned long long *)malloc(n * sizeof(unsigned long long));
+        if (prefix && h && cudaMemcpy(h, s->wave_trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            char path[1200];
+            snprintf(path, sizeof(path), "%s_solver%dx%d.bin", prefix, s->W, s->H);
+            if (FILE *f = fopen(path, "wb")) {
+                const int hdr[2] = {s->wave_trace_npass, WAVE_MAX_CTAS};
+                fwrite(hdr, sizeof(int), 2, f);
+                fwrite(h, sizeof(unsigned long long), n, f);
+                fclose(f);
+            }
+        }
+        free(h);
+        cudaFree(s->wave_trace);
+    }
     dct_free(s);
     cudaFree(s->sweep_max); cudaFreeHost(s->h_sweep_max);
     cudaFree(s->mask); cudaFree(s->d_flags); cudaFreeHost(s->h_flags);
