@@ -74,6 +74,9 @@ struct pcd_solver {
     double *phi_alt = nullptr;      // device: ping-pong partner of phi on the tiled path
     unsigned *wave_ctl = nullptr;   // device: per-CTA sequence words + error word of the persistent wavefront kernel
     unsigned wave_seq = 0;          // sequence number of the last pass it executed
+    double *d_split = nullptr;      // parity-split copy of D for the TMA staging of the wavefront kernel (sor_tiled.cu)
+    alignas(64) unsigned char dmap[128] = {};   // its tensor map (CUtensorMap)
+    int dmap_state = 0;             // 0 undecided, 1 in use, -1 not available (cp.async staging)
     unsigned long long *wave_trace = nullptr;   // PCD_WAVE_TRACE diagnostics (timestamps of the last launch)
     int wave_trace_npass = 0;
     cudaStream_t aux_stream = nullptr;                         // copies a block's maxima out while the next block runs

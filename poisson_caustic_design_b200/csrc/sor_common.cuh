@@ -77,8 +77,13 @@ struct WavePeer {
     unsigned long long *trace = nullptr;                      // diagnostics (PCD_WAVE_TRACE): per CTA and pass 4 x globaltimer
                                                               // [wait begin, pass begin, pass end, published], else nullptr
 };
+// dmap: tensor map (128 bytes, tiled_dmap_encode) of the parity-split copy of D, or nullptr for the cp.async staging
 int tiled_run_peer(const double *D, int W, int H, int row_first, int rows, int grow0, int sweeps_per_pass,
-                   unsigned long long *slots, const WavePeer &peer, int sm_count, int sm_reserve, cudaStream_t stream);
+                   unsigned long long *slots, const WavePeer &peer, const void *dmap, int sm_count, int sm_reserve,
+                   cudaStream_t stream);
+int tiled_dsplit_pitch(int W);                                                       // column pairs per row of the split copy
+int tiled_dsplit(const double *D, double *S, int W, int rows, cudaStream_t stream);  // S[rows][2][Kp] <- D[rows][W]
+int tiled_dmap_encode(void *map_out, const double *S, int W, int rows);
 int tiled_strips(int W);
 
 }  // namespace pcd

@@ -159,6 +159,15 @@ static int run_tiled(pcd_solver *s, const double *D, double *phi, int max_it, do
             PCD_CUDA(cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming));
         }
     }
+    // D staged by TMA from a parity-split copy (one bulk tensor copy per row and CTA instead of two cp.async per thread)
+    if (!per_pass && s->dmap_state == 0) {
+        s->dmap_state = -1;
+        const size_t n = (size_t)tiled_dsplit_pitch(W) * 2 * H;
+        if (cudaMalloc(&s->d_split, n * sizeof(double)) == cudaSuccess && tiled_dmap_encode(s->dmap, s->d_split, W, H) == PCD_OK) s->dmap_state = 1;
+        else cudaGetLastError();
+    }
+    const void *dmap = (!per_pass && s->dmap_state == 1) ? s->dmap : nullptr;
+    if (dmap) PCD_TRY(tiled_dsplit(D, s->d_split, W, H, s->stream));
     int chunk = s->check_lag > 0 ? s->check_lag : 64;
     chunk = ((chunk + TS - 1) / TS) * TS;  // whole passes
     if (chunk > HALF) chunk = HALF;
@@ -196,7 +205,7 @@ static int run_tiled(pcd_solver *s, const double *D, double *phi, int max_it, do
                         pr.trace = s->wave_trace;
                         s->wave_trace_npass = npass;
                     }
-                    PCD_TRY(tiled_run_peer(D, W, H, 0, H, 0, spp, s->sweep_max + off + j, pr, s->sm_count, 0, s->stream));
+                    PCD_TRY(tiled_run_peer(D, W, H, 0, H, 0, spp, s->sweep_max + off + j, pr, dmap, s->sm_count, 0, s->stream));
                     s->wave_seq += (unsigned)npass;
                     cur ^= (npass & 1);
                     j += npass * spp;
@@ -313,6 +322,7 @@ void solver_free(pcd_solver *s) {
     cudaFree(s->sweep_max); cudaFreeHost(s->h_sweep_max);
     cudaFree(s->mask); cudaFree(s->d_flags); cudaFreeHost(s->h_flags);
     cudaFree(s->res_state); cudaFreeHost(s->h_res_state); cudaFree(s->halo); cudaFree(s->phi_alt); cudaFree(s->wave_ctl);
+    cudaFree(s->d_split);
     if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
     for (int i = 0; i < 2; ++i) {
         if (s->ev_blk[i]) cudaEventDestroy(s->ev_blk[i]);

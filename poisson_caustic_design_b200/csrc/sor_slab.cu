@@ -39,6 +39,9 @@ struct pcd_slab {
     unsigned *ctl = nullptr;              // see CTL_* above
     unsigned *done = nullptr;             // per-CTA sequence words of the persistent pass kernel [WAVE_MAX_CTAS]
     int passes_per_launch = 0;            // 0 = a whole block of sweeps per launch; 1 when a neighbour shares this device
+    double *d_split = nullptr;            // parity-split copy of D (TMA staging of the pass kernel), refreshed when D changes
+    alignas(64) unsigned char dmap[128] = {};
+    bool dmap_ok = false;
     unsigned long long *trace = nullptr;  // PCD_WAVE_TRACE=<prefix>: timestamps of the last launch, dumped at destroy
     int trace_npass = 0;
     double *peer_phi[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [side][buffer], side 0 = up, 1 = down
@@ -154,6 +157,14 @@ int pcd_slab_create(int width, int height, int row0, int rows, int device, void 
         return PCD_ERR_CUDA;
     }
     s->ctl = reinterpret_cast<unsigned *>(s->phi[0] + n);
+    {   // optional: D staged by TMA from a parity-split copy
+        const size_t ns = (size_t)tiled_dsplit_pitch(width) * 2 * (rows + 2 * s->GH);
+        if (cudaMalloc(&s->d_split, ns * sizeof(double)) == cudaSuccess && cudaMemset(s->d_split, 0, ns * sizeof(double)) == cudaSuccess &&
+            tiled_dmap_encode(s->dmap, s->d_split, width, rows + 2 * s->GH) == PCD_OK)
+            s->dmap_ok = true;
+        else
+            cudaGetLastError();
+    }
     *out = s;
     return PCD_OK;
 }
@@ -185,6 +196,7 @@ void pcd_slab_destroy(pcd_slab *s) {
         }
     cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->D); cudaFree(s->mask); cudaFree(s->sweep_max); cudaFree(s->d_flag);
     cudaFree(s->done);
+    cudaFree(s->d_split);
     delete s;
 }
 
@@ -220,6 +232,7 @@ int pcd_slab_upload(pcd_slab *s, const double *D_rows, const double *phi_rows) {
         PCD_LAUNCHED();
         s->launches++;
         PCD_CUDA(cudaMemcpyAsync(&s->has_nan, s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        if (s->dmap_ok) PCD_TRY(tiled_dsplit(s->D, s->d_split, s->W, s->rows + 2 * s->GH, s->stream));
     }
     if (phi_rows) {
         PCD_CUDA(cudaMemcpyAsync(s->phi[0], phi_rows, bytes, cudaMemcpyHostToDevice, s->stream));
@@ -251,6 +264,7 @@ int pcd_slab_load_device(pcd_slab *s, const double *D_full, const double *phi_fu
     PCD_LAUNCHED();
     s->launches++;
     PCD_CUDA(cudaMemcpyAsync(&s->has_nan, s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if (s->dmap_ok) PCD_TRY(tiled_dsplit(s->D, s->d_split, s->W, s->rows + 2 * s->GH, s->stream));
     PCD_CUDA(cudaStreamSynchronize(s->stream));
     return PCD_OK;
 }
@@ -431,7 +445,7 @@ int pcd_slab_peer_run(pcd_slab *s, int nsweeps, int slot) {
             s->trace_npass = npass;
         }
         PCD_TRY(tiled_run_peer(s->D, s->W, s->H, s->row0, s->rows, s->row0 - s->GH, spp, s->sweep_max + slot + j, pr,
-                               s->sm_count, s->sm_reserve, s->stream));
+                               s->dmap_ok ? s->dmap : nullptr, s->sm_count, s->sm_reserve, s->stream));
         s->seq += (unsigned)npass;
         s->cur ^= (npass & 1);
         s->launches++;

@@ -27,9 +27,11 @@
 //
 // Neighbour rule / update / max: src/solver.cpp:29-56 (no NaN holes on this path: the solver falls back to the
 // masked colour kernels when D contains NaN).
+#include <cuda.h>
 #include <cuda_pipeline_primitives.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "sor_common.cuh"
 
@@ -65,6 +67,7 @@ struct WaveParams {
     SorW w;
     unsigned long long *slots;  // per-sweep max: TS entries per pass
     WavePeer peer;              // persistent multi-pass launch + fused ghost-row exchange (PEER kernels only)
+    alignas(64) CUtensorMap dmap;   // DTMA kernels: D in the parity-split layout [row][parity][Kp] as a 2-D tensor (Kp, 2*rows)
 };
 
 // what changes from pass to pass inside one launch
@@ -91,6 +94,40 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
 __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// ---- TMA staging of D (DTMA kernels) -------------------------------------------------------------------------------
+// D is read-only and only ever read by the thread that owns the cell, so its layout is free: the solver keeps a copy in
+// a column-parity-split layout D_split[row][parity][Kp] (Kp = ceil(W/2) rounded up to even) and one elected thread
+// fetches BOTH parity planes of a row's 256 column pairs with ONE bulk tensor copy (cp.async.bulk.tensor.2d, box
+// {256, 2}: 4 KB, zero-filled outside the array, completion on an mbarrier) instead of two 8-byte cp.async per thread.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, int n) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(n));
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(unsigned long long *b, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded: a copy that never lands must not hang the device (the error word voids the launch, like a dead neighbour)
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity, int *err) {
+    if (mbar_try(b, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(b, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            if (err) atomicExch(err, 1);
+            break;
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *b) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(b)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
 // one thread: wait until *flag has reached `want` (sequence numbers only grow).  SYS: the flag is written by another
 // GPU.  A writer that never shows up must not hang the device: after ~3 s the slab's error word is set instead.
 template <bool SYS>
@@ -123,6 +160,7 @@ struct WaveThread {  // per-thread invariants
     bool ex0, ex1, core;
     double cx[2], wx[2];
     int ys, ye, y0, y1;
+    int k0, f_last;   // DTMA: first column pair of the window (tensor coordinate, may be negative); last step of the chunk
 };
 
 // One row step.  C = (f - ys) mod R is compile-time; chunks start so that the active cell of row r in phase ph
@@ -137,12 +175,13 @@ struct WaveThread {  // per-thread invariants
 //                 their own neighbour count.
 constexpr int WAVE_STEADY = 0, WAVE_CHECKED = 1;
 
-template <int TS, int C, int MODE>
+template <int TS, int C, int MODE, bool DTMA>
 __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveDyn &d, const WaveThread &t, const int f,
                                           double (&v)[WaveCfg<TS>::R][2], double *__restrict__ sphi,
-                                          double *__restrict__ sD, double (&lmax)[TS]) {
+                                          double *__restrict__ sD, double (&lmax)[TS], unsigned long long *dbar, unsigned &dpar) {
     using Cfg = WaveCfg<TS>;
     constexpr int R = Cfg::R, NP = Cfg::NP, PITCH = Cfg::PITCH;
+    constexpr int DP = DTMA ? WAVE_NT : PITCH, DO = DTMA ? 0 : 1;   // pitch / first-column offset of a parity row of D
     const int W = p.W, H = p.H, k = t.k;
     // (a) stream row f+PF into ring slot (C+PF)%R, 8-byte cp.async per cell.  Columns outside the grid are never copied
     // and never updated in STEADY blocks: their slots keep the 0.0 the ring was initialised with; CHECKED blocks zero-fill
@@ -157,20 +196,31 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveDyn &d,
             const size_t o0 = a0 ? base + t.gx0 : 0, o1 = a1 ? base + t.gx0 + 1 : 0;
             __pipeline_memcpy_async(sphi + (SL * 2 + 0) * PITCH + 1 + k, d.phi_in + o0, 8, a0 ? 0 : 8);
             __pipeline_memcpy_async(sphi + (SL * 2 + 1) * PITCH + 1 + k, d.phi_in + o1, 8, a1 ? 0 : 8);
-            __pipeline_memcpy_async(sD + (SL * 2 + 0) * PITCH + 1 + k, p.D + o0, 8, a0 ? 0 : 8);
-            __pipeline_memcpy_async(sD + (SL * 2 + 1) * PITCH + 1 + k, p.D + o1, 8, a1 ? 0 : 8);
+            if constexpr (!DTMA) {
+                __pipeline_memcpy_async(sD + (SL * 2 + 0) * PITCH + 1 + k, p.D + o0, 8, a0 ? 0 : 8);
+                __pipeline_memcpy_async(sD + (SL * 2 + 1) * PITCH + 1 + k, p.D + o1, 8, a1 ? 0 : 8);
+            }
         } else {
             const size_t o = (size_t)(fr - p.grow0) * W + t.gx0;
             if (t.ex0) {
                 __pipeline_memcpy_async(sphi + (SL * 2 + 0) * PITCH + 1 + k, d.phi_in + o, 8);
-                __pipeline_memcpy_async(sD + (SL * 2 + 0) * PITCH + 1 + k, p.D + o, 8);
+                if constexpr (!DTMA) __pipeline_memcpy_async(sD + (SL * 2 + 0) * PITCH + 1 + k, p.D + o, 8);
             }
             if (t.ex1) {
                 __pipeline_memcpy_async(sphi + (SL * 2 + 1) * PITCH + 1 + k, d.phi_in + o + 1, 8);
-                __pipeline_memcpy_async(sD + (SL * 2 + 1) * PITCH + 1 + k, p.D + o + 1, 8);
+                if constexpr (!DTMA) __pipeline_memcpy_async(sD + (SL * 2 + 1) * PITCH + 1 + k, p.D + o + 1, 8);
             }
         }
         __pipeline_commit();
+        if constexpr (DTMA) {
+            // both parity planes of D's row fr for the window's 256 column pairs: ONE bulk tensor copy by one thread,
+            // zero-filled outside the array.  Only rows that a later step waits for are requested (<= f_last + 1), so
+            // every mbarrier phase that completes is consumed exactly once.
+            if (k == 0 && (MODE == WAVE_STEADY || fr <= t.f_last + 1)) {
+                mbar_expect(dbar + SL, 2 * WAVE_NT * (unsigned)sizeof(double));
+                tma_load_2d(sD + SL * 2 * WAVE_NT, &p.dmap, t.k0, 2 * (fr - p.grow0), dbar + SL);
+            }
+        }
     }
     // (b) row f becomes active: own pair from the smem ring into the register ring
     v[C][0] = sphi[(C * 2 + 0) * PITCH + 1 + k];
@@ -190,7 +240,7 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveDyn &d,
         if (MODE == WAVE_CHECKED) a = a && r >= 0 && r < H;   // ... and so do rows outside the grid
         act[ph] = a;
         nbv[ph] = q ? sphi[(SL * 2 + 0) * PITCH + 1 + k + 1] : sphi[(SL * 2 + 1) * PITCH + 1 + k - 1];
-        Dvv[ph] = sD[(SL * 2 + q) * PITCH + 1 + k];
+        Dvv[ph] = sD[(SL * 2 + q) * DP + DO + k];
     }
 #pragma unroll
     for (int ph = 0; ph < NP; ++ph) {
@@ -239,17 +289,22 @@ __device__ __forceinline__ void wave_step(const WaveParams &p, const WaveDyn &d,
     }
     // (e) row f+1 must have landed before the next step reads it
     __pipeline_wait_prior(WAVE_PF - 1);
+    if constexpr (DTMA) {
+        constexpr int S1 = (C + 1) % R;
+        mbar_wait(dbar + S1, (dpar >> S1) & 1u, p.peer.err);
+        dpar ^= 1u << S1;
+    }
     __syncthreads();
 }
 
-template <int TS, int C, int MODE>
+template <int TS, int C, int MODE, bool DTMA>
 struct WaveUnroll {
     static __device__ __forceinline__ void run(const WaveParams &p, const WaveDyn &d, const WaveThread &t, const int f,
                                                const int f_last, double (&v)[WaveCfg<TS>::R][2], double *sphi, double *sD,
-                                               double (&lmax)[TS]) {
+                                               double (&lmax)[TS], unsigned long long *dbar, unsigned &dpar) {
         if (MODE != WAVE_STEADY && f + C > f_last) return;  // CTA-uniform: the chunk's last block stops at its last step
-        wave_step<TS, C, MODE>(p, d, t, f + C, v, sphi, sD, lmax);
-        if constexpr (C + 1 < WaveCfg<TS>::R) WaveUnroll<TS, C + 1, MODE>::run(p, d, t, f, f_last, v, sphi, sD, lmax);
+        wave_step<TS, C, MODE, DTMA>(p, d, t, f + C, v, sphi, sD, lmax, dbar, dpar);
+        if constexpr (C + 1 < WaveCfg<TS>::R) WaveUnroll<TS, C + 1, MODE, DTMA>::run(p, d, t, f, f_last, v, sphi, sD, lmax, dbar, dpar);
     }
 };
 
@@ -271,11 +326,26 @@ __device__ __forceinline__ void push_rows(const WaveParams &p, const WaveDyn &d,
     }
 }
 
+// DTMA: D of the first WAVE_PF rows of a chunk (ring slots 0..PF-1).  D never changes during a solve, so a persistent
+// launch requests them BEFORE it waits for its neighbours: the copy's latency hides behind the pass boundary.
+__device__ __forceinline__ void dtma_prologue(const WaveParams &p, const WaveThread &t, double *sD, unsigned long long *dbar) {
+    if (t.k != 0) return;
+#pragma unroll
+    for (int j = 0; j < WAVE_PF; ++j) {
+        const int fr = t.ys + j;
+        if (fr <= t.f_last + 1) {
+            mbar_expect(dbar + j, 2 * WAVE_NT * (unsigned)sizeof(double));
+            tma_load_2d(sD + j * 2 * WAVE_NT, &p.dmap, t.k0, 2 * (fr - p.grow0), dbar + j);
+        }
+    }
+}
+
 // One pass of one CTA over its chunk.  top / bot: this chunk touches the slab's first / last owned rows AND a
 // neighbouring slab is attached there (its ghost rows are fed from here, flag value `seq`).
-template <int TS, bool PEER>
+template <int TS, bool PEER, bool DTMA>
 __device__ __forceinline__ void wave_chunk(const WaveParams &p, const WaveDyn &d, const WaveThread &t, double *sphi, double *sD,
-                                           double (*wred)[WAVE_NT / 32], const bool top, const bool bot, const unsigned seq) {
+                                           double (*wred)[WAVE_NT / 32], const bool top, const bool bot, const unsigned seq,
+                                           unsigned long long *dbar, unsigned &dpar) {
     using Cfg = WaveCfg<TS>;
     constexpr int R = Cfg::R, NP = Cfg::NP, PITCH = Cfg::PITCH;
     const int H = p.H;
@@ -296,11 +366,18 @@ __device__ __forceinline__ void wave_chunk(const WaveParams &p, const WaveDyn &d
         const size_t o0 = a0 ? base + t.gx0 : 0, o1 = a1 ? base + t.gx0 + 1 : 0;
         __pipeline_memcpy_async(sphi + (j * 2 + 0) * PITCH + 1 + t.k, d.phi_in + o0, 8, a0 ? 0 : 8);
         __pipeline_memcpy_async(sphi + (j * 2 + 1) * PITCH + 1 + t.k, d.phi_in + o1, 8, a1 ? 0 : 8);
-        __pipeline_memcpy_async(sD + (j * 2 + 0) * PITCH + 1 + t.k, p.D + o0, 8, a0 ? 0 : 8);
-        __pipeline_memcpy_async(sD + (j * 2 + 1) * PITCH + 1 + t.k, p.D + o1, 8, a1 ? 0 : 8);
+        if constexpr (!DTMA) {
+            __pipeline_memcpy_async(sD + (j * 2 + 0) * PITCH + 1 + t.k, p.D + o0, 8, a0 ? 0 : 8);
+            __pipeline_memcpy_async(sD + (j * 2 + 1) * PITCH + 1 + t.k, p.D + o1, 8, a1 ? 0 : 8);
+        }
         __pipeline_commit();
     }
+    if constexpr (DTMA && !PEER) dtma_prologue(p, t, sD, dbar);   // (a persistent launch requested these rows before its waits)
     __pipeline_wait_prior(WAVE_PF - 1);
+    if constexpr (DTMA) {   // D of row ys (slot 0)
+        mbar_wait(dbar + 0, dpar & 1u, p.peer.err);
+        dpar ^= 1u;
+    }
     __syncthreads();
 
     const int f_last = t.y1 + 2 * (NP - 1);
@@ -310,8 +387,8 @@ __device__ __forceinline__ void wave_chunk(const WaveParams &p, const WaveDyn &d
         // every row streamed in exists
         const int r_min = fb - 1 - 2 * (NP - 1), r_max = fb + R - 2, f_max = fb + R - 1 + WAVE_PF;
         const bool steady = r_min >= max(t.y0, 1) && r_max <= min(t.y1 - 1, H - 2) && f_max <= min(t.ye, H - 1);
-        if (steady) WaveUnroll<TS, 0, WAVE_STEADY>::run(p, d, t, fb, f_last, v, sphi, sD, lmax);
-        else WaveUnroll<TS, 0, WAVE_CHECKED>::run(p, d, t, fb, f_last, v, sphi, sD, lmax);
+        if (steady) WaveUnroll<TS, 0, WAVE_STEADY, DTMA>::run(p, d, t, fb, f_last, v, sphi, sD, lmax, dbar, dpar);
+        else WaveUnroll<TS, 0, WAVE_CHECKED, DTMA>::run(p, d, t, fb, f_last, v, sphi, sD, lmax, dbar, dpar);
         if constexpr (PEER) {
             // The top edge rows are complete long before the chunk is: copy them into the upper neighbour's ghost rows
             // now, and raise its flag ONE BLOCK LATER, when the peer stores have long been acknowledged -- the
@@ -353,14 +430,25 @@ __device__ __forceinline__ void wave_chunk(const WaveParams &p, const WaveDyn &d
     }
 }
 
-template <int TS, bool PEER>
+template <int TS, bool PEER, bool DTMA>
 __global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __grid_constant__ WaveParams p) {
     using Cfg = WaveCfg<TS>;
     constexpr int R = Cfg::R, NP = Cfg::NP, PITCH = Cfg::PITCH;
-    extern __shared__ double smem[];
+    constexpr int SD_ELEMS = DTMA ? R * 2 * WAVE_NT : R * 2 * PITCH;
+    extern __shared__ __align__(128) double smem[];
     double *sphi = smem;                   // [R][2][PITCH]
-    double *sD = smem + R * 2 * PITCH;     // [R][2][PITCH]
+    double *sD = smem + R * 2 * PITCH;     // [R][2][PITCH], DTMA: [R][2][WAVE_NT] dense (128-byte aligned: R*2*PITCH*8 is)
     __shared__ double wred[TS][WAVE_NT / 32];
+    __shared__ unsigned long long dbar[R];   // DTMA: one mbarrier per ring slot of D
+    static_assert(!DTMA || (R * 2 * PITCH * 8) % 128 == 0, "the D ring must start on a 128-byte boundary");
+    unsigned dpar = 0u;                      // DTMA: phase parity of every slot's mbarrier (bit per slot)
+    if constexpr (DTMA) {
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < R; ++i) mbar_init(dbar + i, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&p.dmap) : "memory");
+        }
+    }
 
     WaveThread t;
     t.k = threadIdx.x;
@@ -386,6 +474,8 @@ __global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __gr
     t.ex0 = t.gx0 >= 0 && t.gx0 < W;
     t.ex1 = t.gx0 + 1 >= 0 && t.gx0 + 1 < W;
     t.core = (2 * t.k >= Cfg::HX) && (2 * t.k < Cfg::LXW - Cfg::HX);
+    t.k0 = xw0 / 2;                                                 // xw0 is even (and may be -HX)
+    t.f_last = t.y1 + 2 * (NP - 1);
     {
         const int c0 = 4 - (t.gx0 == 0 ? 1 : 0) - (t.gx0 == W - 1 ? 1 : 0), c1 = 4 - (t.gx0 + 1 == 0 ? 1 : 0) - (t.gx0 + 1 == W - 1 ? 1 : 0);
         t.cx[0] = (double)c0; t.cx[1] = (double)c1;
@@ -393,13 +483,14 @@ __global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __gr
     }
     // the ring is zeroed once: a pass overwrites every slot it reads for a live result, and the two pad columns of a
     // parity row are never written
-    for (int i = t.k; i < 2 * R * 2 * PITCH; i += WAVE_NT) smem[i] = 0.0;
+    for (int i = t.k; i < R * 2 * PITCH + SD_ELEMS; i += WAVE_NT) smem[i] = 0.0;
+    if constexpr (DTMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores above, bulk copies into the same bytes below
     __syncthreads();
 
     if constexpr (!PEER) {
         WaveDyn d;
         d.phi_in = p.phi_in; d.phi_out = p.phi_out; d.up_out = nullptr; d.dn_out = nullptr; d.slots = p.slots;
-        wave_chunk<TS, false>(p, d, t, sphi, sD, wred, false, false, 0u);
+        wave_chunk<TS, false, DTMA>(p, d, t, sphi, sD, wred, false, false, 0u, dbar, dpar);
     } else {
         // ---- persistent launch: p.peer.npass passes, CTAs synchronise with their neighbours only ----
         const int nbx = (int)gridDim.x, nby = (int)gridDim.y, bx = (int)blockIdx.x, by = (int)blockIdx.y;
@@ -416,6 +507,9 @@ __global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __gr
             d.up_out = has_up ? p.peer.up_buf[oid] : nullptr;
             d.dn_out = has_dn ? p.peer.dn_buf[oid] : nullptr;
             d.slots = p.slots + (size_t)i * TS;
+            if constexpr (DTMA) {
+                if (!empty) dtma_prologue(p, t, sD, dbar);   // every warp is past its last read of the D ring (barrier below / kernel start)
+            }
             unsigned long long *tr = nullptr;
             if (p.peer.trace && threadIdx.x == 0) {
                 tr = p.peer.trace + ((size_t)i * WAVE_MAX_CTAS + (by * nbx + bx)) * 4;
@@ -442,12 +536,19 @@ __global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __gr
                 // of this GPU leaves at its next pass boundary instead of spinning ~3 s per pass (the error word is
                 // per GPU; the neighbouring GPUs notice through their own waits)
                 const int dead = __syncthreads_or(threadIdx.x == 0 ? *((volatile int *)p.peer.err) : 0);
-                if (dead) break;
+                if (dead) {
+                    if constexpr (DTMA) {   // do not leave with bulk copies in flight into this CTA's shared memory
+                        if (!empty)
+                            for (int j = 0; j < WAVE_PF; ++j)
+                                if (t.ys + j <= t.f_last + 1) mbar_wait(dbar + j, (dpar >> j) & 1u, nullptr);
+                    }
+                    break;
+                }
                 __threadfence();   // every thread's loads of this pass are ordered behind the flags observed above
             }
             // (2) the pass
             if (tr) tr[1] = global_ns();
-            if (!empty) wave_chunk<TS, true>(p, d, t, sphi, sD, wred, top, bot, seq);
+            if (!empty) wave_chunk<TS, true, DTMA>(p, d, t, sphi, sD, wred, top, bot, seq, dbar, dpar);
             // (3) publish: every store of this CTA's pass is visible before its sequence word moves
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -463,24 +564,24 @@ __global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __gr
 constexpr int TILED_TS = 2;
 int tiled_sweeps_per_pass() { return TILED_TS; }
 
-template <int TS, bool PEER>
+template <int TS, bool PEER, bool DTMA>
 static int wave_smem_optin(size_t smem) {
     // the opt-in is per device: remember which devices have it (contexts on several threads may race here: atomic)
     static std::atomic<unsigned long long> done_mask{0ull};
     int dev = 0;
     PCD_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !((done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
-        PCD_CUDA(cudaFuncSetAttribute(sor_wave_kernel<TS, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PCD_CUDA(cudaFuncSetAttribute(sor_wave_kernel<TS, PEER, DTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
     }
     return PCD_OK;
 }
 
-template <int TS, bool PEER>
+template <int TS, bool PEER, bool DTMA = false>
 static int launch_wave(const WaveParams &prm, int sm_count, int sm_reserve, cudaStream_t stream) {
     using Cfg = WaveCfg<TS>;
-    const size_t smem = (size_t)2 * Cfg::R * 2 * Cfg::PITCH * sizeof(double);
-    PCD_TRY((wave_smem_optin<TS, PEER>(smem)));
+    const size_t smem = (size_t)Cfg::R * 2 * (Cfg::PITCH + (DTMA ? WAVE_NT : Cfg::PITCH)) * sizeof(double);
+    PCD_TRY((wave_smem_optin<TS, PEER, DTMA>(smem)));
     WaveParams p = prm;
     const int strips = (p.W + Cfg::CORE - 1) / Cfg::CORE;
     // ONE wave of two CTAs per SM (never a second, nearly empty wave).  Measured on B200 (2048^2: 59 chunks of 35
@@ -511,9 +612,9 @@ static int launch_wave(const WaveParams &prm, int sm_count, int sm_reserve, cuda
             return PCD_ERR_UNSUPPORTED;
         }
         void *args[] = {&p};
-        PCD_CUDA(cudaLaunchCooperativeKernel((void *)sor_wave_kernel<TS, true>, grid, dim3(WAVE_NT), args, smem, stream));
+        PCD_CUDA(cudaLaunchCooperativeKernel((void *)sor_wave_kernel<TS, true, DTMA>, grid, dim3(WAVE_NT), args, smem, stream));
     } else {
-        sor_wave_kernel<TS, false><<<grid, WAVE_NT, smem, stream>>>(p);
+        sor_wave_kernel<TS, false, false><<<grid, WAVE_NT, smem, stream>>>(p);
     }
     PCD_LAUNCHED();
     return PCD_OK;
@@ -536,13 +637,85 @@ int tiled_pass(const double *phi_in, double *phi_out, const double *D, int W, in
 // ping-ponging between peer.buf[0] and peer.buf[1] (peer.cur holds it first), maxima into slots[0 .. npass *
 // sweeps_per_pass), ghost rows pushed into the attached neighbours (see WavePeer).
 int tiled_run_peer(const double *D, int W, int H, int row_first, int rows, int grow0, int sweeps_per_pass,
-                   unsigned long long *slots, const WavePeer &peer, int sm_count, int sm_reserve, cudaStream_t stream) {
+                   unsigned long long *slots, const WavePeer &peer, const void *dmap, int sm_count, int sm_reserve,
+                   cudaStream_t stream) {
     WaveParams prm;
     prm.phi_in = nullptr; prm.phi_out = nullptr; prm.D = D; prm.W = W; prm.H = H;
     prm.row_first = row_first; prm.rows = rows; prm.grow0 = grow0; prm.nchunks = 1;
     prm.w = make_w(W); prm.slots = slots; prm.peer = peer;
+    // D staged by TMA from its parity-split copy -- where it pays.  Measured on B200 (tools/wave_time.py, us per sweep,
+    // TMA / cp.async): 8192^2 (482 rows per chunk) 153.0 / 156.1, 4096^2 (113) 47.3 / 45.4, 8192 x 1024 (60) 30.2 / 26.4,
+    // 2048^2 (35) 21.9 / 18.0: the bulk copy saves ~50 ns per row step and costs ~9 us per pass (its waits are polled,
+    // the cp.async ones are scoreboard waits), so it wins from roughly 190 rows per chunk on.
+    bool use_tma = dmap != nullptr;
+    if (use_tma) {
+        using Cfg = WaveCfg<TILED_TS>;
+        const int strips = (W + Cfg::CORE - 1) / Cfg::CORE;
+        int chunks = (WAVE_CTAS * sm_count) / strips;
+        if (chunks * 4 * Cfg::NP > rows) chunks = rows / (4 * Cfg::NP);
+        if (chunks < 1) chunks = 1;
+        static const int min_rows = getenv("PCD_WAVE_TMA_MIN_ROWS") ? atoi(getenv("PCD_WAVE_TMA_MIN_ROWS")) : 192;   // tuning knob
+        use_tma = rows / chunks >= min_rows;
+    }
+    if (use_tma) {
+        memcpy(&prm.dmap, dmap, sizeof(CUtensorMap));
+        if (sweeps_per_pass >= 2) return launch_wave<2, true, true>(prm, sm_count, sm_reserve, stream);
+        return launch_wave<1, true, true>(prm, sm_count, sm_reserve, stream);
+    }
+    memset(&prm.dmap, 0, sizeof(CUtensorMap));
     if (sweeps_per_pass >= 2) return launch_wave<2, true>(prm, sm_count, sm_reserve, stream);
     return launch_wave<1, true>(prm, sm_count, sm_reserve, stream);
+}
+
+// ---- parity-split copy of D for the TMA staging ------------------------------------------------------------------
+int tiled_dsplit_pitch(int W) { return (((W + 1) / 2) + 1) & ~1; }   // Kp: column pairs per row, rounded up to even
+
+__global__ void dsplit_kernel(const double *__restrict__ D, double *__restrict__ S, int W, int rows, int Kp) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (k >= Kp) return;
+    const size_t i = (size_t)r * W + 2 * k;
+    S[((size_t)r * 2 + 0) * Kp + k] = 2 * k < W ? D[i] : 0.0;
+    S[((size_t)r * 2 + 1) * Kp + k] = 2 * k + 1 < W ? D[i + 1] : 0.0;
+}
+
+// S[rows][2][Kp] <- D[rows][W] (on `stream`)
+int tiled_dsplit(const double *D, double *S, int W, int rows, cudaStream_t stream) {
+    const int Kp = tiled_dsplit_pitch(W);
+    dsplit_kernel<<<dim3((Kp + 255) / 256, rows), 256, 0, stream>>>(D, S, W, rows, Kp);
+    PCD_LAUNCHED();
+    return PCD_OK;
+}
+
+// The tensor map of a parity-split D: 2-D (Kp, 2 * rows) fp64, box {WAVE_NT, 2}.  `map_out`: 128 bytes, 64-byte aligned
+// not required here (it is copied into the kernel parameters).  Returns PCD_ERR_UNSUPPORTED when the driver entry
+// point is missing or refuses the shape: the caller then runs the cp.async staging.
+int tiled_dmap_encode(void *map_out, const double *S, int W, int rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn enc = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            enc = (EncodeFn)fn;
+        else
+            cudaGetLastError();
+    }
+    static const bool off = getenv("PCD_WAVE_NO_TMA") != nullptr;   // diagnostics: force the cp.async staging
+    if (!enc || off) return PCD_ERR_UNSUPPORTED;
+    const int Kp = tiled_dsplit_pitch(W);
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)2 * rows}, strides[1] = {(cuuint64_t)Kp * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)WAVE_NT, 2}, estr[2] = {1, 1};
+    if (WAVE_NT > 256) return PCD_ERR_UNSUPPORTED;
+    const CUresult rc = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)S, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return PCD_ERR_UNSUPPORTED;
+    memcpy(map_out, &m, sizeof(m));
+    return PCD_OK;
 }
 
 int tiled_strips(int W) { return (W + WaveCfg<TILED_TS>::CORE - 1) / WaveCfg<TILED_TS>::CORE; }
