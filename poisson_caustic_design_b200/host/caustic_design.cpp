@@ -126,13 +126,31 @@ void Caustic_design::pull(int level) {
 
 void Caustic_design::sync_fields() { pull(1); }
 
+// Everything of the public state the reference's next call would read: both point sets of the mesh (all three
+// coordinates) and the warm starts phi and h.  SYNC_ALL calls it before every iteration, so that a caller who edits the
+// public members between calls sees the reference's behaviour; the other sync modes leave the device state alone.
 void Caustic_design::push_mesh() {
     std::vector<double> x, y, z;
     soa(mesh->target_points, x, y, z);
     check(pcd_set_field(ctx, PCD_FIELD_TARGET_X, x.data()), "mesh upload");
     check(pcd_set_field(ctx, PCD_FIELD_TARGET_Y, y.data()), "mesh upload");
+    check(pcd_set_field(ctx, PCD_FIELD_TARGET_Z, z.data()), "mesh upload");
     soa(mesh->source_points, x, y, z);
+    if (x != pushed_sx || y != pushed_sy) {   // the device caches a point-location map of the source mesh: only invalidate it on a real edit
+        check(pcd_set_field(ctx, PCD_FIELD_SOURCE_X, x.data()), "mesh upload");
+        check(pcd_set_field(ctx, PCD_FIELD_SOURCE_Y, y.data()), "mesh upload");
+        pushed_sx = x; pushed_sy = y;
+    }
     check(pcd_set_field(ctx, PCD_FIELD_SOURCE_Z, z.data()), "mesh upload");
+    auto grid_up = [&](const std::vector<std::vector<double>> &g, int field) {
+        if ((int)g.size() != resolution_y || g.empty() || (int)g[0].size() != resolution_x) return;   // not mirrored yet
+        std::vector<double> flat((size_t)resolution_x * resolution_y);
+        for (int yy = 0; yy < resolution_y; ++yy)
+            for (int xx = 0; xx < resolution_x; ++xx) flat[(size_t)yy * resolution_x + xx] = g[yy][xx];
+        check(pcd_set_field(ctx, field, flat.data()), "field upload");
+    };
+    grid_up(phi, PCD_FIELD_PHI);
+    grid_up(h, PCD_FIELD_H);
 }
 
 int Caustic_design::last_solver_sweeps() const {
@@ -203,5 +221,9 @@ void Caustic_design::initialize_solvers(std::vector<std::vector<double>> image) 
     check(pcd_initialize_solvers(ctx, flat.data()), "initialize_solvers");
     std::cout << "built mesh" << std::endl;  // src/caustic_design.cpp:341
     pull(field_sync == SYNC_ALL ? 1 : 0);
+    {
+        std::vector<double> z;
+        soa(mesh->source_points, pushed_sx, pushed_sy, z);
+    }
     std::cout << target_areas.size() << std::endl;  // :350
 }

@@ -98,13 +98,15 @@ class Caustic_design {
     // stages.  Bit-identical to one GPU.  Call before initialize_solvers; an empty list = single GPU.
     void set_devices(const std::vector<int> &devices) { this->devices = devices; if (!devices.empty()) device = devices[0]; }
     void sync_fields();               // pull every public member from the device now
-    void push_mesh();                 // upload mesh->target_points / source_points after the caller edited them
+    void push_mesh();                 // upload what the reference's next call would read from the public members: both
+                                      // point sets of the mesh (x, y, z) and the warm starts phi and h (SYNC_ALL does it itself)
     int last_solver_sweeps() const;   // sweeps of the most recent Poisson solve
 
    private:
     pcd_ctx *ctx;
     pcd_multi *multi;
     std::vector<int> devices;
+    std::vector<double> pushed_sx, pushed_sy;   // source x / y as last uploaded (the device caches a map of the source mesh)
     FieldSync field_sync;
     int device;
     int solver_path;
