@@ -93,13 +93,14 @@ def load_traffic():
         return None
 
 
-def wave_traffic(traffic, cells):
-    """DRAM bytes of one wavefront pass over `cells` cells, scaled from the committed 8192^2 capture; None when the
-    working set (3 arrays) is not far beyond the 126 MB L2, where the capture does not transfer."""
+def wave_traffic(traffic, cells, sweeps_per_launch=2.0):
+    """DRAM bytes of one launch of the wavefront kernel over `cells` cells (a launch = sweeps_per_launch / 2 passes),
+    scaled from the committed 8192^2 capture; None when the working set (3 arrays) is not far beyond the 126 MB L2,
+    where the capture does not transfer."""
     w = (traffic or {}).get("sor_wave_kernel")
     if not w or 24.0 * cells < 4 * 126e6:
         return None
-    return int(w["dram_bytes_per_cell_per_launch"] * cells)
+    return int(w["dram_bytes_per_cell_per_pass"] * cells * sweeps_per_launch / 2.0)
 
 
 class ClockSampler:
@@ -545,7 +546,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     traffic = load_traffic()
     us_per_sweep = kernel_ms * 1e3 / sweeps if sweeps else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (traffic["dram_bytes_per_launch"] if path == "resident" else wave_traffic(traffic, W * H // (world if distributed else 1))) if traffic else None,
+                "traffic": (traffic["dram_bytes_per_launch"] if path == "resident" else wave_traffic(traffic, W * H // (world if distributed else 1), sweeps / max(solve_launches, 1))) if traffic else None,
                 "kernel": {"resident": "sor_resident_kernel", "tiled": "sor_wave_kernel", "dct": "dct_gemm_kernel"}.get(path, "sor_colour_kernel"),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / max(solve_launches, 1) / (world if distributed else 1),
@@ -555,7 +556,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                 "us_per_sweep": us_per_sweep,
                 "note": ("phi and D live in registers/shared memory for the whole solve: DRAM traffic per launch is one read "
                          "of both fields, far below the algorithmic bytes, so HBM is NOT this kernel's roof (see on_chip)" if path == "resident" else
-                         "temporal blocking: each launch applies 2 sweeps per HBM pass (12 B/cell/sweep of real traffic)")}
+                         "temporal blocking: 2 sweeps per HBM pass (12 B/cell/sweep of real traffic), one persistent launch per block of passes")}
     if path == "resident" and (W, H) == (1024, 1024) and us_per_sweep:
         roofline["on_chip"] = dict(RESIDENT_FLOORS_1024, us_per_sweep=us_per_sweep,
                                    frac_of_exchange_floor=RESIDENT_FLOORS_1024["exchange_floor_us_per_sweep"] / us_per_sweep,
@@ -639,7 +640,7 @@ def run_slab(args, rank: int, local_rank: int, world: int):
                            "sweeps_per_step": sweeps_per_step, "l2": "working set 1.6 GB >> L2"},
                 "roofline": {"bound": "hbm", "achieved": rec["per_gpu_algorithmic_gbs"], "peak": peak, "unit": "GB/s",
                              "frac": rec["per_gpu_frac_of_hbm_peak"],
-                             "traffic": wave_traffic(load_traffic(), W * H // world), "kernel": "sor_wave_kernel", "peak_source": peak_src,
+                             "traffic": wave_traffic(load_traffic(), W * H // world, 64), "kernel": "sor_wave_kernel", "peak_source": peak_src,
                              "note": "per-GPU algorithmic GB/s (24 B/cell/sweep); whole job = achieved x n_gpus"},
                 "poisson_gbs": rec["algorithmic_gbs"], "gpu_launches": int(launches * world), "clocks": clocks, "slab": {"c5": rec},
                 "e2e": {"value": rec["sweeps_per_s"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * sweeps_per_step,
