@@ -64,6 +64,7 @@ struct WaveParams {
     int row_first, rows; // owned global rows [row_first, row_first + rows)
     int grow0;           // global row of local row 0 of the arrays
     int nchunks;         // row chunks (not counting the short last chunk of a PEER pass)
+    int top_credit;      // PEER: rows the first chunk gives to the others (it also feeds the upper neighbour's ghost rows)
     SorW w;
     unsigned long long *slots;  // per-sweep max: TS entries per pass
     WavePeer peer;              // persistent multi-pass launch + fused ghost-row exchange (PEER kernels only)
@@ -311,17 +312,23 @@ struct WaveUnroll {
 // Ghost rows of a neighbouring slab: every thread copies ITS OWN two columns of `nrows` finished rows of this pass's
 // output field (it stored them itself a few steps ago) into the neighbour's output field -- plain stores to peer memory
 // over NVLink.  Kept out of the row step so that the hot loop carries neither the code nor the registers for it.
+template <int NROWS>
 __device__ __forceinline__ void push_rows(const WaveParams &p, const WaveDyn &d, const WaveThread &t, double *dst_base,
-                                          const int dst_grow0, const int first_row, const int nrows) {
+                                          const int dst_grow0, const int first_row) {
     if (!t.core || !(t.ex0 || t.ex1)) return;
-    for (int r = first_row; r < first_row + nrows; ++r) {
-        const double *src = d.phi_out + (size_t)(r - p.grow0) * p.W + t.gx0;
-        double *dst = dst_base + (size_t)(r - dst_grow0) * p.W + t.gx0;
-        if (t.ex0 && t.ex1 && ((p.W & 1) == 0)) {
-            *reinterpret_cast<double2 *>(dst) = __ldcg(reinterpret_cast<const double2 *>(src));
-        } else {
-            if (t.ex0) dst[0] = __ldcg(src);
-            if (t.ex1) dst[1] = __ldcg(src + 1);
+    const double *src = d.phi_out + (size_t)(first_row - p.grow0) * p.W + t.gx0;
+    double *dst = dst_base + (size_t)(first_row - dst_grow0) * p.W + t.gx0;
+    if (t.ex0 && t.ex1 && ((p.W & 1) == 0)) {      // all loads first (L2 round trips overlap), then all peer stores
+        double2 v[NROWS];
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r) v[r] = __ldcg(reinterpret_cast<const double2 *>(src + (size_t)r * p.W));
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r) *reinterpret_cast<double2 *>(dst + (size_t)r * p.W) = v[r];
+    } else {
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r) {
+            if (t.ex0) dst[(size_t)r * p.W] = __ldcg(src + (size_t)r * p.W);
+            if (t.ex1) dst[(size_t)r * p.W + 1] = __ldcg(src + (size_t)r * p.W + 1);
         }
     }
 }
@@ -398,16 +405,16 @@ __device__ __forceinline__ void wave_chunk(const WaveParams &p, const WaveDyn &d
                 up_sent = true;
             }
             if (top && !up_pushed && r_min + R - 1 >= p.row_first + p.peer.gh - 1) {
-                push_rows(p, d, t, d.up_out, p.peer.up_grow0, p.row_first, p.peer.gh);
+                push_rows<2 * TS + 1>(p, d, t, d.up_out, p.peer.up_grow0, p.row_first);
                 up_pushed = true;
             }
         }
     }
     if constexpr (PEER) {
-        if (top && !up_pushed) push_rows(p, d, t, d.up_out, p.peer.up_grow0, p.row_first, p.peer.gh);
+        if (top && !up_pushed) push_rows<2 * TS + 1>(p, d, t, d.up_out, p.peer.up_grow0, p.row_first);
         if (top && !up_sent) strip_signal(p.peer.sig_up + blockIdx.x, seq);
         if (bot) {
-            push_rows(p, d, t, d.dn_out, p.peer.dn_grow0, p.row_first + p.rows - p.peer.gh, p.peer.gh);
+            push_rows<2 * TS + 1>(p, d, t, d.dn_out, p.peer.dn_grow0, p.row_first + p.rows - p.peer.gh);
             strip_signal(p.peer.sig_dn + blockIdx.x, seq);
         }
     }
@@ -459,8 +466,12 @@ __global__ void __launch_bounds__(WAVE_NT, WAVE_CTAS) sor_wave_kernel(const __gr
         t.y0 = t.y1 - p.peer.tail_rows;
     } else {
         const int main_rows = p.rows - (PEER ? p.peer.tail_rows : 0);   // balanced split: chunk lengths differ by <= 1 row
-        t.y0 = p.row_first + (int)blockIdx.y * main_rows / p.nchunks;
-        t.y1 = p.row_first + ((int)blockIdx.y + 1) * main_rows / p.nchunks;
+        // ... except that the first chunk of a slab with an upper neighbour is `top_credit` rows shorter: it spends that time
+        // copying its first rows into the neighbour and raising the flag, and a pass moves at the pace of its slowest CTA
+        const int c = (int)blockIdx.y, n = p.nchunks, cr = (PEER && n > 1) ? p.top_credit : 0;
+        auto cut = [&](int i) { return i == 0 ? 0 : (int)((long long)i * (main_rows + cr) / n) - cr; };
+        t.y0 = p.row_first + cut(c);
+        t.y1 = p.row_first + (c + 1 == n ? main_rows : cut(c + 1));
     }
     const bool empty = t.y0 >= t.y1;
     if (!PEER && empty) return;
@@ -597,13 +608,25 @@ static int launch_wave(const WaveParams &prm, int sm_count, int sm_reserve, cuda
     if constexpr (PEER) {
         // with a lower neighbour the bottom rows get a short chunk of their own (they are the LAST rows a chunk
         // walking down would finish), so that the neighbour has them long before the pass ends
-        if (p.peer.dn_buf[0] && p.rows >= 8 * min_rows && chunks >= 3) { tail = 2 * Cfg::NP + 4; chunks -= 1; }
+        // (its CTAs would otherwise idle for most of the pass: 32 rows where the slab is thick enough, measured -1.3 %)
+        static const int tail_env = getenv("PCD_WAVE_TAIL_ROWS") ? atoi(getenv("PCD_WAVE_TAIL_ROWS")) : 0;     // tuning knob
+        if (p.peer.dn_buf[0] && p.rows >= 8 * min_rows && chunks >= 3) {
+            tail = tail_env >= 2 * Cfg::NP + 1 ? tail_env : (p.rows >= 16 * 32 ? 32 : 2 * Cfg::NP + 4);
+            chunks -= 1;
+        }
         p.peer.tail_rows = tail;
     }
+    // The first chunk of a slab with an upper neighbour also copies its first rows into the neighbour and raises the flag:
+    // ~8 us per pass, and a pass moves at the pace of its slowest CTA (profiles/r02_wave_trace_*: 52 us against 42-46 for
+    // the other chunks).  It gets 10 rows fewer, the others share them: 8192 x 1024 slabs on 4 GPUs 30.6 -> 28.8 us/sweep.
+    static const int credit_env = getenv("PCD_WAVE_TOP_CREDIT") ? atoi(getenv("PCD_WAVE_TOP_CREDIT")) : 10;   // tuning knob
+    p.top_credit = 0;
+    if (PEER && p.peer.up_buf[0]) p.top_credit = credit_env;
     const int main_rows = p.rows - tail;
     if (chunks * min_rows > main_rows) chunks = main_rows / min_rows;
     if (chunks < 1) chunks = 1;
     p.nchunks = chunks;
+    if (chunks < 2 || p.top_credit < 0 || (main_rows + p.top_credit) / chunks - p.top_credit < 2 * min_rows) p.top_credit = 0;
     const dim3 grid(strips, chunks + (tail ? 1 : 0));
     if constexpr (PEER) {
         // persistent: every CTA must be resident (they wait for each other)
@@ -627,7 +650,7 @@ int tiled_pass(const double *phi_in, double *phi_out, const double *D, int W, in
                int nsweeps, unsigned long long *slots, int sm_count, int sm_reserve, cudaStream_t stream) {
     WaveParams prm;
     prm.phi_in = phi_in; prm.phi_out = phi_out; prm.D = D; prm.W = W; prm.H = H;
-    prm.row_first = row_first; prm.rows = rows; prm.grow0 = grow0; prm.nchunks = 1;
+    prm.row_first = row_first; prm.rows = rows; prm.grow0 = grow0; prm.nchunks = 1; prm.top_credit = 0;
     prm.w = make_w(W); prm.slots = slots;
     if (nsweeps >= 2) return launch_wave<2, false>(prm, sm_count, sm_reserve, stream);
     return launch_wave<1, false>(prm, sm_count, sm_reserve, stream);
@@ -641,7 +664,7 @@ int tiled_run_peer(const double *D, int W, int H, int row_first, int rows, int g
                    cudaStream_t stream) {
     WaveParams prm;
     prm.phi_in = nullptr; prm.phi_out = nullptr; prm.D = D; prm.W = W; prm.H = H;
-    prm.row_first = row_first; prm.rows = rows; prm.grow0 = grow0; prm.nchunks = 1;
+    prm.row_first = row_first; prm.rows = rows; prm.grow0 = grow0; prm.nchunks = 1; prm.top_credit = 0;
     prm.w = make_w(W); prm.slots = slots; prm.peer = peer;
     // D staged by TMA from its parity-split copy -- where it pays.  Measured on B200 (tools/wave_time.py, us per sweep,
     // TMA / cp.async): 8192^2 (482 rows per chunk) 153.0 / 156.1, 4096^2 (113) 47.3 / 45.4, 8192 x 1024 (60) 30.2 / 26.4,

@@ -1,5 +1,6 @@
 // Exercises the C++ drop-in API exactly the way reference callers use it (src/solver.h:8,
 // src/caustic_design.h:7-66): reads a raw problem from argv[1], writes results to argv[2].
+#include <algorithm>
 #include <cstdio>
 #include <fstream>
 #include <vector>
@@ -34,6 +35,12 @@ int main(int argc, char **argv) {
     for (auto &p : cd.mesh->target_points) out.write((char *)p.data(), 24);
     for (auto &r : cd.phi) out.write((char *)r.data(), 8 * W);
     out.write((char *)cd.errors.data(), 8 * cd.errors.size());
+    // the public members belong to the caller (src/caustic_design.h:16-30): put the mesh back on the source lattice and
+    // zero the warm start -- the next iteration must then repeat iteration 0
+    cd.mesh->target_points = cd.mesh->source_points;
+    for (auto &r : cd.phi) std::fill(r.begin(), r.end(), 0.0);
+    const double again = cd.perform_transport_iteration();
+    out.write((char *)&again, 8);
     cd.perform_height_map_iteration(0);
     for (auto &p : cd.mesh->source_points) out.write((char *)p.data(), 24);
     for (auto &r : cd.h) out.write((char *)r.data(), 8 * W);

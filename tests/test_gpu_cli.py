@@ -97,6 +97,7 @@ def test_cpp_drop_in_api(pcd, port, oracle_mod, tmp_path):
     tp = take(3 * V, (V, 3))
     phi2 = take(W * H, (H, W))
     errors = take(V)
+    again = take(1)[0]
     sp = take(3 * V, (V, 3))
     h = take(W * H, (H, W))
     caught = int(np.frombuffer(buf[off:off + 4].tobytes(), dtype=np.int32)[0])
@@ -106,10 +107,13 @@ def test_cpp_drop_in_api(pcd, port, oracle_mod, tmp_path):
     od.initialize_solvers(img)
     want = [od.transport_iteration() for _ in range(2)]
     assert np.abs(steps - want).max() < 1e-6 * max(want)
+    assert again == steps[0]          # edits of the public members (mesh put back, phi zeroed) are honoured: iteration 0 repeats
     disp = np.abs(od.get("target_x") - od.get("source_x")).max()
     assert np.abs(tp[:, 0] - od.get("target_x")).max() < 1e-6 * disp and np.abs(tp[:, 1] - od.get("target_y")).max() < 1e-6 * disp
     assert np.abs(errors - od.get("errors")).max() < 1e-6 * np.abs(od.get("errors")).max()
     assert phi2.shape == (H, W) and np.isfinite(phi2).all()
+    od.set("target_x", od.get("source_x")); od.set("target_y", od.get("source_y")); od.set("phi", np.zeros((H, W)))
+    assert abs(od.transport_iteration() - again) < 1e-6 * again
     od.height_iteration(0)
     zr = od.get("source_z")
     assert np.abs(sp[:, 2] - zr).max() <= 5e-4 * (zr.max() - zr.min())

@@ -107,6 +107,31 @@ def test_fused_exchange_on_one_gpu_bit_identical(pcd, port, shape, G, sweeps):
     assert np.array_equal(got2, single_gpu(pcd, D, phi0, 5)[0]) and info2["sweeps"] == 5
 
 
+def test_fused_exchange_production_geometry(pcd):
+    """8192-wide slabs of 1024 rows -- the geometry of the 8192^2 problem on eight GPUs, where the launcher shortens the
+    first chunk of a slab with an upper neighbour (it also feeds that neighbour's ghost rows) and gives the bottom rows a
+    32-row chunk of their own: two such slabs on one GPU against the single-GPU per-colour kernels."""
+    from poisson_caustic_design_b200 import slab
+    rng = np.random.RandomState(8)
+    H, W, G, sweeps = 2048, 8192, 2, 9
+    D = rng.standard_normal((H, W))
+    D -= D.mean()
+    phi0 = rng.standard_normal((H, W))
+    engines = []
+    for g in range(G):
+        row0, rows = slab.partition(H, G, g)
+        e = slab.CudaSlabEngine(W, H, row0, rows, 0)
+        e.upload(slab.with_ghosts(D, row0, rows, e.GH), slab.with_ghosts(phi0, row0, rows, e.GH))
+        engines.append(e)
+    info = slab.solve_local_peer(engines, sweeps, 0.0, 16)
+    got = np.concatenate([e.download() for e in engines], axis=0)
+    for e in engines:
+        e.close()
+    want, winfo = single_gpu(pcd, D, phi0, sweeps)
+    assert info["sweeps"] == sweeps and np.array_equal(got, want)
+    assert info["last_max_update"] == winfo["last_max_update"]
+
+
 @pytest.mark.parametrize("mode", ["peer", "wavefront", "colour"])
 def test_two_gpu_nccl_run(pcd, tmp_path, mode):
     if pcd.device_count() < 2:

@@ -1,18 +1,15 @@
 #!/bin/bash
-mkdir -p gpurun_out/r02g
+mkdir -p gpurun_out/r02r
 cd /root/repo
-timeout 400 python bench.py --gpus 8 --no-cpu > gpurun_out/r02g/bench_g8.json 2> gpurun_out/r02g/bench_g8.err; echo "bench g8 rc=$?"
-timeout 300 python bench.py --gpus 4 --no-cpu > gpurun_out/r02g/bench_g4.json 2> gpurun_out/r02g/bench_g4.err; echo "bench g4 rc=$?"
-for ce in 64 512; do
-  timeout 200 python bench.py --gpus 8 --workload c5slab --steps 16 --warmup 1 --check-every $ce > gpurun_out/r02g/slab_g8_ce$ce.json 2> gpurun_out/r02g/slab_g8_ce$ce.err
-done
+timeout 200 python bench.py --gpus 8 --no-cpu 2>gpurun_out/r02r/bench_g8.err | grep '^{' > gpurun_out/r02r/bench_g8.json; echo "g8 rc=$?"
+timeout 150 python bench.py --gpus 4 --no-cpu 2>gpurun_out/r02r/bench_g4.err | grep '^{' > gpurun_out/r02r/bench_g4.json; echo "g4 rc=$?"
+timeout 150 python bench.py --gpus 2 --no-cpu 2>gpurun_out/r02r/bench_g2.err | grep '^{' > gpurun_out/r02r/bench_g2.json; echo "g2 rc=$?"
+PCD_WAVE_TRACE=gpurun_out/r02r/trace8 timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node=8 --master-addr 127.0.0.1 --master-port 29551 tools/slab_run.py --W 8192 --H 8192 --sweeps 128 --check_every 64 2>&1 | grep us_per_sweep
+python tools/wave_trace.py gpurun_out/r02r/trace8_row*.bin --strips 17 --json gpurun_out/r02r/trace8_summary.json > /dev/null
 python - <<'PY'
-import json,glob
-def load(f):
-    for line in open(f):
-        if line.startswith('{'): return json.loads(line)
-for f in sorted(glob.glob('gpurun_out/r02g/*.json')):
+import json
+for n in (8,4,2):
     try:
-        d=load(f); s=d.get('slab',{}); print(f, round(d['value'],2), {k:(round(v['us_per_sweep'],2), v['mode']) for k,v in s.items()})
-    except Exception as e: print(f, 'ERR', e)
+        d=json.load(open(f'gpurun_out/r02r/bench_g{n}.json')); print(n, round(d['value'],2), round(d['e2e']['value'],2), {k:(round(v['us_per_sweep'],2), v['mode'], v['bit_identical_to_1gpu']) for k,v in d['slab'].items()})
+    except Exception as e: print(n, 'ERR', e)
 PY
