@@ -158,6 +158,7 @@ static int gemm(const double *A, const double *B, double *C, int M, int N, int K
 // solver plumbing
 // ------------------------------------------------------------------------------------------------
 struct DctState {
+    bool ready = false;
     double *CW = nullptr, *CWt = nullptr, *CH = nullptr, *CHt = nullptr;   // DCT-II matrices and their transposes
     double *lx = nullptr, *ly = nullptr;                                   // eigenvalues per column / row index
     double *T = nullptr, *S = nullptr;                                     // H x W temporaries
@@ -166,16 +167,20 @@ struct DctState {
 void dct_free(pcd_solver *s) {
     DctState *d = static_cast<DctState *>(s->dct_state);
     if (!d) return;
-    cudaFree(d->CW); cudaFree(d->CWt);
     if (d->CH != d->CW) { cudaFree(d->CH); cudaFree(d->CHt); }
     if (d->ly != d->lx) cudaFree(d->ly);
+    cudaFree(d->CW); cudaFree(d->CWt);
     cudaFree(d->lx); cudaFree(d->T); cudaFree(d->S);
+    cudaGetLastError();
     delete d;
     s->dct_state = nullptr;
 }
 
 static int dct_prepare(pcd_solver *s, pcd_solve_info *info) {
-    if (s->dct_state) return PCD_OK;
+    if (s->dct_state) {
+        if (static_cast<DctState *>(s->dct_state)->ready) return PCD_OK;
+        dct_free(s);   // an earlier attempt failed half way (out of memory): start over
+    }
     const int W = s->W, H = s->H;
     DctState *d = new DctState();
     s->dct_state = d;
@@ -201,6 +206,7 @@ static int dct_prepare(pcd_solver *s, pcd_solve_info *info) {
     }
     PCD_CUDA(cudaMalloc(&d->T, sizeof(double) * (size_t)W * H));
     PCD_CUDA(cudaMalloc(&d->S, sizeof(double) * (size_t)W * H));
+    d->ready = true;
     return PCD_OK;
 }
 

@@ -33,6 +33,7 @@ struct pcd_multi {
     pcd_solver fallback;                         // single-GPU solver on devices[0]: NaN holes, slabs too thin
     bool fallback_ready = false;
     pcd_ctx *attached = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;      // device time of a solve, on streams[0]
 };
 
 using namespace pcd;
@@ -134,6 +135,7 @@ void pcd_multi_destroy(pcd_multi *m) {
     for (cudaEvent_t e : m->ev_blk) cudaEventDestroy(e);
     for (cudaEvent_t e : m->ev_copied) cudaEventDestroy(e);
     if (m->fallback_ready) { cudaSetDevice(m->dev[0]); solver_free(&m->fallback); }
+    if (m->e0) { cudaSetDevice(m->dev[0]); cudaEventDestroy(m->e0); cudaEventDestroy(m->e1); }
     delete m;
 }
 
@@ -171,11 +173,12 @@ int pcd_multi_solve(pcd_multi *m, const double *D_dev, double *phi_dev, int max_
         return solver_run(&m->fallback, D_dev, phi_dev, max_iterations, tol, info);
     }
     const int TS = pcd_slab_sweeps_per_pass();
-    cudaEvent_t e0, e1;
     PCD_TRY(select_device(m->dev[0]));
-    PCD_CUDA(cudaEventCreate(&e0));
-    PCD_CUDA(cudaEventCreate(&e1));
-    PCD_CUDA(cudaEventRecord(e0, m->streams[0]));
+    if (!m->e0) {
+        PCD_CUDA(cudaEventCreate(&m->e0));
+        PCD_CUDA(cudaEventCreate(&m->e1));
+    }
+    PCD_CUDA(cudaEventRecord(m->e0, m->streams[0]));
     // Blocks of check_every sweeps; the stopping rule is evaluated ONE BLOCK LATE (block b+1 is queued before the maxima
     // of block b are read; they leave on the slabs' side streams), so no GPU drains between blocks.  Same schedule as
     // the single-GPU large-grid solver (run_tiled) => same bits.
@@ -233,12 +236,10 @@ int pcd_multi_solve(pcd_multi *m, const double *D_dev, double *phi_dev, int max_
         PCD_CUDA(cudaStreamSynchronize(m->streams[g]));
     }
     PCD_TRY(select_device(m->dev[0]));
-    PCD_CUDA(cudaEventRecord(e1, m->streams[0]));
-    PCD_CUDA(cudaEventSynchronize(e1));
+    PCD_CUDA(cudaEventRecord(m->e1, m->streams[0]));
+    PCD_CUDA(cudaEventSynchronize(m->e1));
     float ms = 0.f;
-    PCD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    PCD_CUDA(cudaEventElapsedTime(&ms, m->e0, m->e1));
     info->sweeps = done;
     info->converged_at = conv;
     info->last_max_update = last;

@@ -716,17 +716,14 @@ int tiled_dmap_encode(void *map_out, const double *S, int W, int rows) {
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn enc = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static const EncodeFn enc = []() -> EncodeFn {   // resolved once (thread-safe static initialisation)
         cudaDriverEntryPointQueryResult q;
         void *fn = nullptr;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            enc = (EncodeFn)fn;
-        else
-            cudaGetLastError();
-    }
+            return (EncodeFn)fn;
+        cudaGetLastError();
+        return nullptr;
+    }();
     static const bool off = getenv("PCD_WAVE_NO_TMA") != nullptr;   // diagnostics: force the cp.async staging
     if (!enc || off) return PCD_ERR_UNSUPPORTED;
     const int Kp = tiled_dsplit_pitch(W);
