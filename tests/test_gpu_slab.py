@@ -148,6 +148,23 @@ def test_two_gpu_nccl_run(pcd, tmp_path, mode):
     assert np.array_equal(z["phi"], want)
 
 
+def test_two_gpu_soak(pcd, tmp_path):
+    """10^5 sweeps of the fused peer protocol on two real GPUs (3 125 persistent launches of 16 passes each, per-strip
+    NVLink flags, one-block-late stopping rule with the maxima copied out on a side stream) against one GPU."""
+    if pcd.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    script = os.path.join(ROOT, "tools", "slab_run.py")
+    out = tmp_path / "soak.npz"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29535", script, "--W", "1536", "--H", "1100", "--sweeps", "100000", "--check_every", "32", "--out", str(out),
+           "--mode", "peer"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    z = np.load(out)
+    want, _ = single_gpu(pcd, z["D"], z["phi0"], 100000)
+    assert np.array_equal(z["phi"], want)
+
+
 def _design(pcd, res_w, aspect, seed, device=0):
     from poisson_caustic_design_b200 import synth
     W = 4 * res_w
