@@ -168,3 +168,23 @@ def test_folded_mesh_end_to_end_vs_oracle(pcd, port, oracle_mod):
     print(f"folded={folded} vertex diff {d / disp:.3e} of max displacement, z diff {np.abs(z - zr).max() / (zr.max() - zr.min()):.3e} of range")
     cd.close()
     od.close()
+
+
+def test_height_tolerance_knob(pcd, oracle_mod, golden):
+    """pcd_set_tolerances: the height solves stop at 1e-9 by default and at the reference's 1e-8 on request.  On C1's
+    first height problem red-black sweeps meet 1e-8 after 1 075 sweeps and 1e-9 after 1 572
+    (tests/test_oracle_golden.py::test_height_truncation_evidence); the design on the device must reproduce both."""
+    O = oracle_mod
+    gray = O.rgba_to_gray(golden("images")["siggraph"])
+    s, resized = O.prepare_image(gray, 100, O.f32(0.5), O.f32(1.5), O.f32(0.1))
+    got = {}
+    for tol in (0.0, 1e-8):
+        cd = pcd.from_setup(s)
+        cd.initialize_solvers(resized)
+        if tol:
+            cd.set_tolerances(0.0, tol)
+        cd.run_transport(50, O.f32(0.01))
+        cd.perform_height_map_iteration(0)
+        got[tol] = cd.last_solve_info()["converged_at"]
+        cd.close()
+    assert abs(got[0.0] - 1572) <= 3 and abs(got[1e-8] - 1075) <= 3, got
