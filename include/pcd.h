@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PCD_ABI_VERSION 1
+#define PCD_ABI_VERSION 2   /* 2: per-slab SM reserve, persistent peer run, pcd_multi_*, tolerances, DCT backend (round 2) */
 
 typedef enum pcd_status {
     PCD_OK = 0,

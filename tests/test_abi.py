@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(pcd):
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/pcd.h but not exported"
     assert sorted(n for n, _, _ in pcd.ABI) == syms, "python binding table out of sync with include/pcd.h"
-    assert pcd.lib().pcd_abi_version() == 1
+    assert pcd.lib().pcd_abi_version() == 2
 
 
 def test_no_cpu_fallback(pcd):
