@@ -266,7 +266,9 @@ def run_reference(args, rank: int, world: int):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": cpu.desc, "mesh": [setup.mesh_nx, setup.mesh_ny], "domain": [setup.res_x, setup.res_y],
                    "conv_tres": CONV_TRES,
-                   "parallelism": f"cpu threads={cpu.threads} (reference tile grid)"},
+                   "schedule": "consecutive iterations of complete designs from iteration 0 (re-initialised, untimed, at convergence)",
+                   "parallelism": f"cpu threads={cpu.threads} (reference tile grid)",
+                   "l2": "n/a (host arm)", "solver_path": "reference poisson_solver (lexicographic SOR, thread tiles)", "backend": "sor"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.threads, "kind": cpu.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "step_sizes": sizes[:4], "s_per_step": [round(x, 3) for x in times], "init_s": t_init,
