@@ -228,8 +228,8 @@ int pcd_slab_peer_error_to(pcd_slab *s, double *dst_dev);
  * kernel through peer access.  pcd_multi_solve has the contract of pcd_solver_run with DEVICE arrays on devices[0];
  * pcd_multi_attach installs it as the Poisson solver of a context created on devices[0] (pcd_set_solve_hook), so the
  * reference call it stands behind is poisson_solver as issued at src/caustic_design.cpp:222,311.  Bit-identical to
- * the single-GPU large-grid solver.  NaN holes, or slabs thinner than 2 * pcd_slab_ghost_rows() rows, run on
- * devices[0] alone.  Destroy (or detach) the solver before the context it is attached to. */
+ * the single-GPU large-grid solver.  NaN holes, slabs thinner than 2 * pcd_slab_ghost_rows() rows, or devices
+ * without peer access to each other run on devices[0] alone (same result).  Destroy (or detach) the solver before the context it is attached to. */
 typedef struct pcd_multi pcd_multi;
 int pcd_multi_create(int width, int height, const int *devices, int n_devices, pcd_multi **out);
 void pcd_multi_destroy(pcd_multi *m);

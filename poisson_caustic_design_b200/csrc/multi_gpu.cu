@@ -101,9 +101,13 @@ int pcd_multi_create(int width, int height, const int *devices, int n_devices, p
         }
     }
     if (rc == PCD_OK && m->peers)
-        for (int g = 0; g + 1 < n_devices && rc == PCD_OK; ++g) {
+        for (int g = 0; g + 1 < n_devices && rc == PCD_OK && m->peers; ++g) {
             rc = pcd_slab_peer_connect_local(m->slabs[g], 1, m->slabs[g + 1]);
             if (rc == PCD_OK) rc = pcd_slab_peer_connect_local(m->slabs[g + 1], 0, m->slabs[g]);
+            if (rc == PCD_ERR_UNSUPPORTED) {   // no peer access between two of the devices: every solve runs on devices[0] alone
+                m->peers = false;
+                rc = PCD_OK;
+            }
         }
     if (rc == PCD_OK) {
         // the full fields live on devices[0]: let every other device read / write them directly where it can (the
