@@ -27,13 +27,13 @@
 //
 // Neighbour rule / update / max: src/solver.cpp:29-56 (no NaN holes on this path: the solver falls back to the
 // masked colour kernels when D contains NaN).
-#include <cuda.h>
 #include <cuda_pipeline_primitives.h>
 
 #include <cstdlib>
 #include <cstring>
 
 #include "sor_common.cuh"
+#include "tma.cuh"
 
 namespace pcd {
 
@@ -100,35 +100,6 @@ __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
 // a column-parity-split layout D_split[row][parity][Kp] (Kp = ceil(W/2) rounded up to even) and one elected thread
 // fetches BOTH parity planes of a row's 256 column pairs with ONE bulk tensor copy (cp.async.bulk.tensor.2d, box
 // {256, 2}: 4 KB, zero-filled outside the array, completion on an mbarrier) instead of two 8-byte cp.async per thread.
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *b, int n) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(n));
-}
-__device__ __forceinline__ void mbar_expect(unsigned long long *b, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(unsigned long long *b, unsigned parity) {
-    unsigned ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// bounded: a copy that never lands must not hang the device (the error word voids the launch, like a dead neighbour)
-__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity, int *err) {
-    if (mbar_try(b, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try(b, parity)) {
-        if (clock64() - t0 > 4000000000ll) {
-            if (err) atomicExch(err, 1);
-            break;
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *b) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-                 "l"(map), "r"(smem_u32(b)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-
 // one thread: wait until *flag has reached `want` (sequence numbers only grow).  SYS: the flag is written by another
 // GPU.  A writer that never shows up must not hang the device: after ~3 s the slab's error word is set instead.
 template <bool SYS>
@@ -713,29 +684,10 @@ int tiled_dsplit(const double *D, double *S, int W, int rows, cudaStream_t strea
 // not required here (it is copied into the kernel parameters).  Returns PCD_ERR_UNSUPPORTED when the driver entry
 // point is missing or refuses the shape: the caller then runs the cp.async staging.
 int tiled_dmap_encode(void *map_out, const double *S, int W, int rows) {
-    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static const EncodeFn enc = []() -> EncodeFn {   // resolved once (thread-safe static initialisation)
-        cudaDriverEntryPointQueryResult q;
-        void *fn = nullptr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            return (EncodeFn)fn;
-        cudaGetLastError();
-        return nullptr;
-    }();
     static const bool off = getenv("PCD_WAVE_NO_TMA") != nullptr;   // diagnostics: force the cp.async staging
-    if (!enc || off) return PCD_ERR_UNSUPPORTED;
+    if (off || WAVE_NT > 256) return PCD_ERR_UNSUPPORTED;
     const int Kp = tiled_dsplit_pitch(W);
-    CUtensorMap m;
-    const cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)2 * rows}, strides[1] = {(cuuint64_t)Kp * sizeof(double)};
-    const cuuint32_t box[2] = {(cuuint32_t)WAVE_NT, 2}, estr[2] = {1, 1};
-    if (WAVE_NT > 256) return PCD_ERR_UNSUPPORTED;
-    const CUresult rc = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)S, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) return PCD_ERR_UNSUPPORTED;
-    memcpy(map_out, &m, sizeof(m));
-    return PCD_OK;
+    return tma_encode_2d_f64(map_out, S, (unsigned long long)Kp, (unsigned long long)2 * rows, (unsigned long long)Kp * sizeof(double), WAVE_NT, 2);
 }
 
 int tiled_strips(int W) { return (W + WaveCfg<TILED_TS>::CORE - 1) / WaveCfg<TILED_TS>::CORE; }
