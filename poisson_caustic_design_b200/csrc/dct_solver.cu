@@ -18,7 +18,10 @@
 // masked sweeps then).  Selected explicitly with PCD_SOLVER_DCT; AUTO never picks it.
 #include <cuda_pipeline_primitives.h>
 
+#include <cstdlib>
+
 #include "sor_common.cuh"
+#include "tma.cuh"
 
 namespace pcd {
 
@@ -145,8 +148,123 @@ dct_gemm_kernel(const double *__restrict__ A, const double *__restrict__ B, doub
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same GEMM with both operand tiles staged by TMA: one elected thread issues two bulk tensor copies per k-tile
+// (A box {TBK, GBM}, B box {GBN, TBK}; out-of-range parts zero-filled, so the main loop has no edge predicates), three
+// stages, completion on one mbarrier per stage; the other 255 threads never touch a global address before the epilogue.
+// Needs K and N even (16-byte global row pitches); otherwise the cp.async kernel above runs.
+// ------------------------------------------------------------------------------------------------
+constexpr int TBK = 16, TST = 3;
+constexpr int TSTAGE_DOUBLES = GBM * TBK + TBK * GBN;   // 24 KB per stage
+
+struct GemmMaps {
+    alignas(64) CUtensorMap a, b;
+};
+
+template <bool SCALE>
+__global__ void __launch_bounds__(GNT, 2)
+dct_gemm_tma_kernel(const __grid_constant__ GemmMaps maps, double *__restrict__ C, int M, int N, int K,
+                    const double *__restrict__ ly, const double *__restrict__ lx) {
+    extern __shared__ __align__(128) double tsm[];   // [TST] x { As[GBM][TBK], Bs[TBK][GBN] }
+    __shared__ unsigned long long full[TST];
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+    const int nk = (K + TBK - 1) / TBK;
+    if (t == 0) {
+        for (int i = 0; i < TST; ++i) mbar_init(full + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int kt) {
+        const int st = kt % TST;
+        double *as = tsm + st * TSTAGE_DOUBLES, *bs = as + GBM * TBK;
+        mbar_expect(full + st, TSTAGE_DOUBLES * (unsigned)sizeof(double));
+        tma_load_2d(as, &maps.a, kt * TBK, m0, full + st);
+        tma_load_2d(bs, &maps.b, n0, kt * TBK, full + st);
+    };
+    if (t == 0)
+        for (int kt = 0; kt < TST && kt < nk; ++kt) issue(kt);
+
+    double acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+
+    for (int kt = 0; kt < nk; ++kt) {
+        const int st = kt % TST;
+        mbar_wait(full + st, (unsigned)(kt / TST) & 1u, nullptr);
+        const double *as = tsm + st * TSTAGE_DOUBLES + (ty * 4) * TBK;
+        const double *bs = tsm + st * TSTAGE_DOUBLES + GBM * TBK + tx * 2;
+#pragma unroll
+        for (int k = 0; k < TBK; ++k) {
+            double a[4], b[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = as[i * TBK + k];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const double2 v = *reinterpret_cast<const double2 *>(bs + k * GBN + 32 * p);
+                b[2 * p] = v.x;
+                b[2 * p + 1] = v.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = __fma_rn(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();                                   // every thread is done with stage st
+        if (t == 0 && kt + TST < nk) issue(kt + TST);      // ... so it can be refilled (generic reads -> bulk write: ordered by the barrier)
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+        const double lym = SCALE ? ly[m] : 0.0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int n = n0 + tx * 2 + 32 * p;
+            double v0 = acc[i][2 * p], v1 = acc[i][2 * p + 1];
+            if (SCALE) {
+                if (n < N) v0 = (m == 0 && n == 0) ? 0.0 : -v0 / (lym + lx[n]);
+                if (n + 1 < N) v1 = -v1 / (lym + lx[n + 1]);
+            }
+            if (n + 1 < N) *reinterpret_cast<double2 *>(C + (size_t)m * N + n) = make_double2(v0, v1);   // N is even here
+            else if (n < N) C[(size_t)m * N + n] = v0;
+        }
+    }
+}
+
+static int gemm_tma(const double *A, const double *B, double *C, int M, int N, int K, const double *ly, const double *lx,
+                    cudaStream_t st) {
+    static const bool off = getenv("PCD_DCT_NO_TMA") != nullptr;   // diagnostics
+    if (off || (K & 1) || (N & 1)) return PCD_ERR_UNSUPPORTED;
+    GemmMaps maps;
+    if (tma_encode_2d_f64(&maps.a, A, (unsigned long long)K, (unsigned long long)M, (unsigned long long)K * sizeof(double), TBK, GBM) != PCD_OK ||
+        tma_encode_2d_f64(&maps.b, B, (unsigned long long)N, (unsigned long long)K, (unsigned long long)N * sizeof(double), GBN, TBK) != PCD_OK)
+        return PCD_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)TST * TSTAGE_DOUBLES * sizeof(double);
+    static std::atomic<unsigned long long> optin{0ull};
+    int dev = 0;
+    PCD_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !((optin.load(std::memory_order_acquire) >> dev) & 1ull)) {
+        PCD_CUDA(cudaFuncSetAttribute(dct_gemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PCD_CUDA(cudaFuncSetAttribute(dct_gemm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev < 64) optin.fetch_or(1ull << dev, std::memory_order_release);
+    }
+    const dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM);
+    if (ly) dct_gemm_tma_kernel<true><<<grid, GNT, smem, st>>>(maps, C, M, N, K, ly, lx);
+    else dct_gemm_tma_kernel<false><<<grid, GNT, smem, st>>>(maps, C, M, N, K, nullptr, nullptr);
+    PCD_LAUNCHED();
+    return PCD_OK;
+}
+
 static int gemm(const double *A, const double *B, double *C, int M, int N, int K, const double *ly, const double *lx,
                 cudaStream_t st) {
+    {
+        const int rc = gemm_tma(A, B, C, M, N, K, ly, lx, st);
+        if (rc != PCD_ERR_UNSUPPORTED) return rc;
+    }
     const dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM);
     if (ly) dct_gemm_kernel<true><<<grid, GNT, 0, st>>>(A, B, C, M, N, K, ly, lx);
     else dct_gemm_kernel<false><<<grid, GNT, 0, st>>>(A, B, C, M, N, K, nullptr, nullptr);
