@@ -41,6 +41,7 @@ struct ResState {  // device control block of the resident kernel (mirrored in p
 
 // sor_resident.cu
 int resident_plan(pcd_solver *s);   // 1 when the grid fits the on-chip path (fills s->res_*)
+int resident_slots();               // halo slots (16 B each) per CTA link and direction
 int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double tol, pcd_solve_info *info);
 
 

@@ -290,7 +290,7 @@ int solver_init(pcd_solver *s, int W, int H, int device, int path, cudaStream_t 
         PCD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
         if (coop && resident_plan(s)) {
             s->path_used = PCD_SOLVER_RESIDENT;
-            PCD_CUDA(cudaMalloc(&s->halo, (size_t)s->res_ctas * 2 * W * sizeof(uint4)));
+            PCD_CUDA(cudaMalloc(&s->halo, (size_t)s->res_ctas * 2 * resident_slots() * sizeof(uint4)));
         } else if (path == PCD_SOLVER_RESIDENT) {
             set_error("poisson solver: grid %dx%d does not fit the resident path on this device", W, H);
             return PCD_ERR_UNSUPPORTED;

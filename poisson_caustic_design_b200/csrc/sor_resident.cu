@@ -37,6 +37,10 @@ namespace pcd {
 constexpr int RES_NT = 512;     // 16 warps = 4 per SM sub-partition -> 128 registers per thread
 constexpr int RES_NR_MAX = 7;   // rows per slab (2*NR phi + 2*NR D doubles per thread)
 constexpr int RES_KP = RES_NT + 4;  // smem pitch of one parity row: compile-time so every smem offset is an immediate
+// Halo slots of one link and direction: [parity][RES_NT] x 16 B, the message of column x = 2k+q in slot q * RES_NT + k.
+// Dense per parity: the 32 messages a warp sends in a phase fill 16 whole 32-byte sectors (with one slot per COLUMN, as
+// in round 1, every message half-filled a sector of its own: twice the L2 sector traffic and partial-sector writes).
+constexpr int RES_SLOTS = 2 * RES_NT;
 
 struct ResParams {
     double *phi;              // global field, in/out
@@ -49,7 +53,7 @@ struct ResParams {
     int lag;                  // convergence lag
     double tol;
     SorW w;
-    uint4 *ll;                // LL halo slots: [P][2][W] x 16 B  ([.][0] = from the CTA above, [.][1] = from below)
+    uint4 *ll;                // LL halo slots: [P][2][RES_SLOTS] x 16 B  ([.][0] = from the CTA above, [.][1] = from below)
     unsigned long long *g_max;   // [max_it] per-sweep max|delta| bit patterns
     unsigned long long *g_slot;  // [max_it] low 32: CTAs arrived, high 32: CTAs whose max >= tol
     ResState *state;
@@ -200,13 +204,13 @@ __device__ __forceinline__ void res_phase(Strip<NR> &s, double *__restrict__ smk
     if constexpr (NR >= 2) okb = res_cell<NR, P0, FAST, EDGE, NR - 1>(s, nb[NR - 1], hu, hd, p, lmax);
     if (ok0) {
         smk[(0 * 2 + q0) * RES_KP] = s.v[0][q0];
-        if (ll_up) ll_store(ll_up + 2 * k + q0, s.v[0][q0], seq);
-        if (NR == 1 && ll_dn) ll_store(ll_dn + 2 * k + q0, s.v[0][q0], seq);
+        if (ll_up) ll_store(ll_up + q0 * RES_NT + k, s.v[0][q0], seq);
+        if (NR == 1 && ll_dn) ll_store(ll_dn + q0 * RES_NT + k, s.v[0][q0], seq);
     }
     if constexpr (NR >= 2) {
         if (okb) {
             smk[((NR - 1) * 2 + qb) * RES_KP] = s.v[NR - 1][qb];
-            if (ll_dn) ll_store(ll_dn + 2 * k + qb, s.v[NR - 1][qb], seq);
+            if (ll_dn) ll_store(ll_dn + qb * RES_NT + k, s.v[NR - 1][qb], seq);
         }
     }
 }
@@ -225,9 +229,9 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
     for (int i = tid; i < NR * 2 * Kp; i += RES_NT) smem[i] = 0.0;
     // CTA pairs (clusters of two): the slots of the link INSIDE the pair live in shared memory behind the strip arrays
     // (same offset in both CTAs); the partner writes them through DSMEM and this CTA polls its own shared memory
-    uint4 *pslot = reinterpret_cast<uint4 *>(smem + p.nr_big * 2 * Kp);   // [2][W]: from the CTA above / from below
+    uint4 *pslot = reinterpret_cast<uint4 *>(smem + p.nr_big * 2 * Kp);   // [2][RES_SLOTS]: from the CTA above / from below
     if (p.pair)
-        for (int i = tid; i < 2 * W; i += RES_NT) pslot[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < 2 * RES_SLOTS; i += RES_NT) pslot[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid < 16) arrive[tid] = 0u;
     if (tid == 0) s_stop = 0;
     __syncthreads();
@@ -273,18 +277,18 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
         s.wT[q] = wsel(p.w, cT); s.wM[q] = wsel(p.w, cM); s.wB[q] = wsel(p.w, cB);
     }
 
-    uint4 *ll_up = has_up ? p.ll + ((size_t)(cta - 1) * 2 + 1) * W : nullptr;   // neighbour above: its "from below" slots
-    uint4 *ll_dn = has_dn ? p.ll + ((size_t)(cta + 1) * 2 + 0) * W : nullptr;   // neighbour below: its "from above" slots
-    const uint4 *in_top = p.ll + ((size_t)cta * 2 + 0) * W;
-    const uint4 *in_bot = p.ll + ((size_t)cta * 2 + 1) * W;
+    uint4 *ll_up = has_up ? p.ll + ((size_t)(cta - 1) * 2 + 1) * RES_SLOTS : nullptr;   // neighbour above: its "from below" slots
+    uint4 *ll_dn = has_dn ? p.ll + ((size_t)(cta + 1) * 2 + 0) * RES_SLOTS : nullptr;   // neighbour below: its "from above" slots
+    const uint4 *in_top = p.ll + ((size_t)cta * 2 + 0) * RES_SLOTS;
+    const uint4 *in_bot = p.ll + ((size_t)cta * 2 + 1) * RES_SLOTS;
     if (p.pair) {
         cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
         const int rank = cta % p.pair;
         if (rank != 0) {                          // the CTA above is in this cluster: its "from below" slots, my "from above"
-            ll_up = cl.map_shared_rank(pslot + W, rank - 1); in_top = pslot;
+            ll_up = cl.map_shared_rank(pslot + RES_SLOTS, rank - 1); in_top = pslot;
         }
         if (rank != p.pair - 1 && has_dn) {       // the CTA below is in this cluster
-            ll_dn = cl.map_shared_rank(pslot, rank + 1); in_bot = pslot + W;
+            ll_dn = cl.map_shared_rank(pslot, rank + 1); in_bot = pslot + RES_SLOTS;
         }
     }
     if (idle) { ll_up = nullptr; ll_dn = nullptr; }
@@ -318,9 +322,9 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
             const int p0 = (r0 + colour) & 1;
             if (!idle) {
                 // slots of this phase's halo cells: column of the active cell of row 0 / row NR-1
-                const int xt = 2 * k + p0, xb = 2 * k + ((p0 + NR - 1) & 1);
-                const uint4 *it = (has_up && xt < W) ? in_top + xt : nullptr;
-                const uint4 *ib = (has_dn && xb < W) ? in_bot + xb : nullptr;
+                const int qb = (p0 + NR - 1) & 1, xt = 2 * k + p0, xb = 2 * k + qb;
+                const uint4 *it = (has_up && xt < W) ? in_top + p0 * RES_NT + k : nullptr;
+                const uint4 *ib = (has_dn && xb < W) ? in_bot + qb * RES_NT + k : nullptr;
                 const bool first = seq == 1u;
                 if (p0 == 0) {
                     if (fast) res_phase<NR, 0, true, EDGE>(s, smk, hu, hd, p, lmax, k, ll_up, ll_dn, seq, it, ib, first);
@@ -421,6 +425,8 @@ __global__ void __launch_bounds__(RES_NT, 1) sor_resident_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+int resident_slots() { return RES_SLOTS; }
+
 int resident_plan(pcd_solver *s) {
     const int W = s->W, H = s->H;
     const int K = (W + 1) / 2;
@@ -436,7 +442,7 @@ int resident_plan(pcd_solver *s) {
     const int Kp = RES_KP;
     s->res_ctas = P;
     s->res_rows_per_cta = pick;
-    s->res_smem = (size_t)pick * 2 * Kp * sizeof(double) + (size_t)2 * W * sizeof(uint4);  // + slots of the links inside a cluster
+    s->res_smem = (size_t)pick * 2 * Kp * sizeof(double) + (size_t)2 * RES_SLOTS * sizeof(uint4);  // + slots of the links inside a cluster
     s->res_threads = RES_NT;
     return 1;
 }
@@ -493,7 +499,7 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
         const int k = max_it - done < RES_MAX_SWEEPS_PER_LAUNCH ? max_it - done : RES_MAX_SWEEPS_PER_LAUNCH;
         PCD_CUDA(cudaMemsetAsync(g_max, 0, sizeof(unsigned long long) * (size_t)k, s->stream));
         PCD_CUDA(cudaMemsetAsync(g_slot, 0, sizeof(unsigned long long) * (size_t)k, s->stream));
-        PCD_CUDA(cudaMemsetAsync(s->halo, 0, (size_t)P * 2 * W * sizeof(uint4), s->stream));
+        PCD_CUDA(cudaMemsetAsync(s->halo, 0, (size_t)P * 2 * RES_SLOTS * sizeof(uint4), s->stream));
         PCD_CUDA(cudaMemsetAsync(s->res_state, 0, sizeof(ResState), s->stream));
         ResParams prm;
         prm.phi = phi; prm.D = D; prm.W = W; prm.H = H; prm.K = (W + 1) / 2;
