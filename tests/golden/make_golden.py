@@ -11,6 +11,7 @@ committed, this script is their provenance.
     python tests/golden/make_golden.py solver             # poisson_solver known-answer cases
     python tests/golden/make_golden.py c4                 # BASELINE.json configs[3] (the bench workload): 2 iterations
     python tests/golden/make_golden.py c1height           # C1's first height problem: divergence + the reference's h
+    python tests/golden/make_golden.py c5stages           # BASELINE.json configs[4]: the non-solver stages at 8192^2 / mesh 2048^2
 """
 from __future__ import annotations
 
@@ -287,6 +288,42 @@ def cmd_c1height():
     print("c1height ok", n)
 
 
+def cmd_c5stages():
+    """BASELINE.json configs[4] (synthetic 8192x8192 density, mesh 2048x2048): a CPU solve is out of reach (~85 000
+    sweeps), but every OTHER stage of the first transport iteration is not -- target areas (Sutherland-Hodgman over 4 M
+    vertices), dual-cell areas / errors, the BVH rasteriser, mean removal.  The reference design is created with
+    nthreads = 0: its poisson_solver then runs no tile and returns at once (src/solver.cpp:73-83,142), everything else
+    is the stock code.  Sub-sampled to keep the fixture small."""
+    from poisson_caustic_design_b200 import synth
+    ref = O.RefLib()
+    W = H = 8192
+    img = synth.synth_density(W, H, 8192)
+    st = synth.Setup(2048, W, H, mesh_width=1.0, focal_l=1.5, thickness=0.2)
+    s = O.Setup(st.mesh_nx, st.mesh_ny, st.res_x, st.res_y, st.width, st.height, st.focal_l, st.thickness)
+    d = ref.design(s, threads=0)
+    t0 = time.time()
+    d.initialize_solvers(img)
+    print(f"[c5] init {time.time() - t0:.0f}s", flush=True)
+    ta = d.get("target_areas")
+    step = d.transport_iteration()
+    print(f"[c5] iteration (no solve) {time.time() - t0:.0f}s step {step}", flush=True)
+    err = d.get("errors")
+    ras = d.get("raster")
+    out = {"params": np.array([s.mesh_nx, s.mesh_ny, s.res_x, s.res_y, s.width, s.height, s.focal_l, s.thickness]),
+           "image_md5": np.frombuffer(__import__("hashlib").md5(img.tobytes()).hexdigest().encode(), dtype=np.uint8),
+           "vertex_sub": np.array([16]), "grid_sub": np.array([64]),
+           "target_areas_sum": np.array([ta.sum()]), "target_areas_max": np.array([ta.max()]),
+           "target_areas_sub16": np.ascontiguousarray(ta.reshape(s.mesh_ny, s.mesh_nx)[::16, ::16]).ravel(),
+           "errors_sub16": np.ascontiguousarray(err.reshape(s.mesh_ny, s.mesh_nx)[::16, ::16]).ravel(),
+           "errors_absmax": np.array([np.abs(err).max()]),
+           "raster_sub64": np.ascontiguousarray(ras[::64, ::64]), "raster_absmax": np.array([np.abs(ras).max()]),
+           "raster_rows": np.ascontiguousarray(ras[[0, 1, 4095, 8190, 8191], ::8]),
+           "step": np.array([step]), "wall_s": np.array([time.time() - t0])}
+    d.close()
+    np.savez_compressed(os.path.join(GOLD, "c5_stages.npz"), **out)
+    print(f"[c5] done in {time.time() - t0:.0f}s")
+
+
 if __name__ == "__main__":
     cmd = sys.argv[1]
     if cmd == "images":
@@ -301,6 +338,8 @@ if __name__ == "__main__":
         cmd_c4()
     elif cmd == "c1height":
         cmd_c1height()
+    elif cmd == "c5stages":
+        cmd_c5stages()
     elif cmd == "trim":
         cmd_trim()
     else:

@@ -188,3 +188,36 @@ def test_height_tolerance_knob(pcd, oracle_mod, golden):
         got[tol] = cd.last_solve_info()["converged_at"]
         cd.close()
     assert abs(got[0.0] - 1572) <= 3 and abs(got[1e-8] - 1075) <= 3, got
+
+
+def test_c5_stages_match_reference(pcd, golden):
+    """BASELINE.json configs[4] (synthetic 8192x8192 density, mesh 2048x2048): the non-solver stages of the first
+    transport iteration at FULL size against the reference itself (tests/golden/c5_stages.npz: oracle/_ref with its
+    solver switched off by nthreads = 0) -- target areas over 4 M vertices, dual-cell areas / errors, the rasteriser on
+    67 M samples, mean removal.  The mesh is still the regular lattice, so everything is reassociation-level."""
+    path = os.path.join(GOLD, "c5_stages.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated yet")
+    import hashlib
+    from poisson_caustic_design_b200 import synth
+    g = golden("c5_stages")
+    img = synth.synth_density(8192, 8192, 8192)
+    assert hashlib.md5(img.tobytes()).hexdigest().encode() == g["image_md5"].tobytes()
+    st = synth.Setup(2048, 8192, 8192, mesh_width=1.0, focal_l=1.5, thickness=0.2)
+    cd = pcd.from_setup(st)
+    cd.initialize_solvers(img)
+    del img
+    ny, nx = st.mesh_ny, st.mesh_nx
+    ta = cd.get("target_areas")
+    assert abs(ta.sum() - g["target_areas_sum"][0]) < 1e-11
+    tas = np.ascontiguousarray(ta.reshape(ny, nx)[::16, ::16]).ravel()
+    assert np.abs(tas - g["target_areas_sub16"]).max() <= 1e-12 * g["target_areas_max"][0] * 10
+    cd.stage_errors()
+    cd.stage_raster()
+    cd.stage_subtract_average()
+    err = np.ascontiguousarray(cd.get("errors").reshape(ny, nx)[::16, ::16]).ravel()
+    assert np.abs(err - g["errors_sub16"]).max() <= 1e-10 * g["errors_absmax"][0]
+    ras = cd.get("raster")
+    assert np.abs(ras[::64, ::64] - g["raster_sub64"]).max() <= 1e-9 * g["raster_absmax"][0]
+    assert np.abs(ras[[0, 1, 4095, 8190, 8191], ::8] - g["raster_rows"]).max() <= 1e-9 * g["raster_absmax"][0]
+    cd.close()
