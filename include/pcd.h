@@ -170,6 +170,9 @@ int pcd_solver_store_device(pcd_solver *s, double *phi_dev);
 int pcd_solver_set_check_lag(pcd_solver *s, int check_lag);
 int pcd_solver_run(pcd_solver *s, int max_iterations, double convergence_threshold, pcd_solve_info *info);
 int pcd_solver_path_used(const pcd_solver *s);
+/* Which resident kernel the last pcd_solver_run used: 0 = none (another path), 1 = one neighbour exchange per colour
+ * phase, 2 = one per sweep (deep halos: even width, no NaN holes, more than two rows per CTA).  Same results. */
+int pcd_solver_resident_exchange(const pcd_solver *s);
 
 /* ---- row-slab solver for multi-GPU runs (no counterpart in the reference) -------------------
  * One process per GPU owns global rows [row0, row0+rows) of a width x height grid plus GH =

@@ -93,6 +93,7 @@ ABI = [
     ("pcd_solver_set_check_lag", C.c_int, [C.c_void_p, C.c_int]),
     ("pcd_solver_run", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.POINTER(pcd_solve_info)]),
     ("pcd_solver_path_used", C.c_int, [C.c_void_p]),
+    ("pcd_solver_resident_exchange", C.c_int, [C.c_void_p]),
     ("pcd_slab_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     ("pcd_slab_destroy", None, [C.c_void_p]),
     ("pcd_slab_device_ptrs", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
@@ -227,6 +228,11 @@ class Solver:
         info = pcd_solve_info()
         _check(lib().pcd_solver_run(self._h, int(max_iterations), float(tol), C.byref(info)))
         return info.as_dict()
+
+    @property
+    def resident_exchange(self) -> int:
+        """Resident kernel of the last run: 0 none, 1 one exchange per colour phase, 2 one per sweep (deep halos)."""
+        return lib().pcd_solver_resident_exchange(self._h)
 
 
 class MultiGpuSolver:

@@ -424,6 +424,8 @@ int pcd_solver_run(pcd_solver *s, int max_iterations, double convergence_thresho
 
 int pcd_solver_path_used(const pcd_solver *s) { return s ? s->path_used : -1; }
 
+int pcd_solver_resident_exchange(const pcd_solver *s) { return s ? s->res_exchange : -1; }
+
 int pcd_poisson_solver(const double *D, double *phi, int width, int height, int max_iterations,
                        double convergence_threshold, int device, pcd_solve_info *info) {
     if (!D || !phi) { set_error("null field"); return PCD_ERR_INVALID; }

@@ -342,6 +342,7 @@ int solver_run(pcd_solver *s, const double *D, double *phi, int max_iterations, 
     if (!info) info = &local;
     *info = pcd_solve_info{};
     info->path = s->path_used;
+    s->res_exchange = 0;
     PCD_TRY(select_device(s->device));
     if (max_iterations <= 0) return PCD_OK;  // the reference's loop body never runs (src/solver.cpp:92)
     PCD_CUDA(cudaEventRecord(s->ev0, s->stream));

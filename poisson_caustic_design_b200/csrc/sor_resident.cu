@@ -29,6 +29,7 @@
 #include <cooperative_groups.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "sor_common.cuh"
 
@@ -89,6 +90,16 @@ __device__ __forceinline__ double ll_consume(uint4 r, const uint4 *p, unsigned s
     while (r.y != seq || r.w != seq) {
         r = ll_issue(p);
         if (res_give_up(spins, err)) break;
+    }
+    return __longlong_as_double((long long)(((unsigned long long)r.z << 32) | r.x));
+}
+
+// the same for a thread that keeps going after a voided launch: once it has given up it does not wait again
+__device__ __forceinline__ double ll_consume(uint4 r, const uint4 *p, unsigned seq, int *err, bool &dead) {
+    unsigned spins = 0u;
+    while ((r.y != seq || r.w != seq) && !dead) {
+        r = ll_issue(p);
+        if (res_give_up(spins, err)) dead = true;
     }
     return __longlong_as_double((long long)(((unsigned long long)r.z << 32) | r.x));
 }
@@ -345,7 +356,9 @@ __device__ __forceinline__ void res_body(const ResParams &p, const int r0) {
                 }
                 // the warps of a CTA drift apart by up to 15 phases (below): the stop is announced RES_STOP_AHEAD sweeps
                 // ahead so that every warp of every CTA leaves after the same sweep
-                if ((conv_at == e + 1 && e >= 0) || errv) *((volatile int *)&s_stop) = sweep + 1 + RES_STOP_AHEAD;
+                // (announced once: a void launch keeps errv set, and re-announcing every sweep would never stop)
+                if ((conv_at == e + 1 && e >= 0) || (errv && *((volatile int *)&s_stop) == 0))
+                    *((volatile int *)&s_stop) = sweep + 1 + RES_STOP_AHEAD;
             }
             // After a phase a warp only depends on its two neighbouring warps (the left / right cells of its first and
             // last lane): two rounds of pairwise named barriers (pairs (0,1),(2,3).. then (1,2),(3,4)..) instead of a
@@ -423,9 +436,349 @@ __global__ void __launch_bounds__(RES_NT, 1) sor_resident_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Deep-halo variant (round 2): ONE neighbour exchange per sweep instead of one per colour phase.
+//
+// The chain that paces the kernel above is message latency: a boundary cell of phase p needs the neighbour's boundary
+// cell of phase p-1, i.e. two L2 round trips per sweep lie on the critical path (~1500 cycles each, tools/ll_latency.cu)
+// against ~600 cycles of arithmetic.  Here every CTA also keeps the colour-0 cells of the row just outside its slab
+// on either side (rows r0-1 and r0+NR) and updates them REDUNDANTLY -- same inputs, same expression, same bits as the
+// owner's update -- so the colour-1 phase needs nothing from outside, and a sweep exchanges once: after its colour-1
+// phase a CTA sends the colour-1 cells of its two outermost rows on either side (2 x K messages per link and sweep,
+// the same volume as before).  The schedule of a sweep:
+//   colour 0: rows 1..NR-2 (own data only) | consume the messages | halo row above, rows 0 and NR-1, halo row below
+//   colour 1: rows 0, 1, NR-2, NR-1 -> send | rows 2..NR-3
+// so a message is in flight during (NR-4) + (NR-2) row updates, and one latency per sweep is left on the chain.
+// The colour-1 cell of the halo row that belongs to thread k-1 / k+1 comes from the neighbouring lane by shuffle; the
+// first / last lane of a warp polls that slot itself.  Slots are double-buffered by sweep parity: the sender of
+// message s+2 has consumed the receiver's message s+1, which was sent after message s had been consumed.
+// Limits: even W, no NaN holes, every slab >= 2 rows and the first >= 3 (H > 2 * CTAs): anything else runs the kernel
+// above (a NaN found while loading voids the launch with ResState::error = 2 and the host repeats it there).
+// ------------------------------------------------------------------------------------------------
+constexpr int RES2_SLOTS = 4 * RES_NT;   // [sweep parity][0: row next to the receiver, 1: the row behind it][RES_NT]
+constexpr int RES_ERR_UNSUPPORTED = 2;
+
+template <int A, int B, class F>
+__device__ __forceinline__ void static_rows(F &&f) {
+    if constexpr (A < B) {
+        f(std::integral_constant<int, A>{});
+        static_rows<A + 1, B>(f);
+    }
+}
+
+__device__ __forceinline__ double sor_cell(const double val, const double l, const double u, const double r, const double d,
+                                           const double cnt, const double wv, const double Dv, double &lmax) {
+    const double sum = ((l + u) + r) + d;  // ghosts are 0.0: identical to skipping them
+    const double delta = wv * ((sum - cnt * val) - Dv);
+    const double ad = fabs(delta);
+    if (ad > lmax) lmax = ad;
+    return val + delta;
+}
+
+template <int NR>
+struct DeepStrip {
+    double v[NR][2], D[NR][2];
+    double cM[2], wM[2], cT[2], wT[2], cB[2], wB[2];   // T / B only live in the first / last slab
+    double hu, hd, Du, Dd;   // colour-0 cell of the halo rows r0-1 / r0+NR in this thread's column pair, and its D
+};
+
+// update of the colour-C cell of slab row J (P0 = column parity of the colour-0 cell of row 0)
+template <int NR, int P0, bool EDGE, int C, int J>
+__device__ __forceinline__ void deep_cell(DeepStrip<NR> &s, const double nb, const double upv, const double dnv, double &lmax) {
+    constexpr int q = (P0 + C + J) & 1;
+    const double own = s.v[J][q ^ 1];
+    const double l = (q == 0) ? nb : own, r = (q == 0) ? own : nb;
+    const double u = (J == 0) ? upv : s.v[(J == 0) ? 0 : J - 1][q];
+    const double d = (J == NR - 1) ? dnv : s.v[(J == NR - 1) ? J : J + 1][q];
+    const double cnt = (EDGE && J == 0) ? s.cT[q] : ((EDGE && J == NR - 1) ? s.cB[q] : s.cM[q]);
+    const double wv = (EDGE && J == 0) ? s.wT[q] : ((EDGE && J == NR - 1) ? s.wB[q] : s.wM[q]);
+    s.v[J][q] = sor_cell(s.v[J][q], l, u, r, d, cnt, wv, s.D[J][q], lmax);
+}
+
+template <int P0, int C, int J>
+__device__ __forceinline__ double deep_nb(const double *__restrict__ smk) {
+    constexpr int q = (P0 + C + J) & 1;
+    return (q == 0) ? smk[(J * 2 + 1) * RES_KP - 1] : smk[(J * 2 + 0) * RES_KP + 1];
+}
+
+// rows [A, B) of colour C: all shared-memory reads, then the arithmetic, then the writes
+template <int NR, int P0, bool EDGE, int C, int A, int B>
+__device__ __forceinline__ void deep_rows(DeepStrip<NR> &s, double *__restrict__ smk, const double upv, const double dnv, double &lmax) {
+    if constexpr (A < B) {
+        double nb[B - A];
+        static_rows<A, B>([&](auto Jc) {
+            constexpr int J = decltype(Jc)::value;
+            nb[J - A] = deep_nb<P0, C, J>(smk);
+        });
+        static_rows<A, B>([&](auto Jc) {
+            constexpr int J = decltype(Jc)::value;
+            deep_cell<NR, P0, EDGE, C, J>(s, nb[J - A], upv, dnv, lmax);
+        });
+        static_rows<A, B>([&](auto Jc) {
+            constexpr int J = decltype(Jc)::value, q = (P0 + C + J) & 1;
+            smk[(J * 2 + q) * RES_KP] = s.v[J][q];
+        });
+    }
+}
+
+template <int NR, int P0, bool EDGE>
+__device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
+    static_assert(NR >= 2, "deep halos need two rows per slab");
+    extern __shared__ double smem[];  // [NR][2][Kp] as in res_body, then the slots of the links inside a cluster
+    __shared__ unsigned arrive[16];
+    __shared__ int s_stop;
+
+    const int tid = threadIdx.x, cta = blockIdx.x, k = tid, lane = tid & 31;
+    const int W = p.W, H = p.H, K = p.K;
+    constexpr int Kp = RES_KP;
+    const bool has_up = !EDGE || cta > 0, has_dn = !EDGE || cta + 1 < p.P;
+    int *const err = &p.state->error;
+
+    for (int i = tid; i < NR * 2 * Kp; i += RES_NT) smem[i] = 0.0;
+    uint4 *pslot = reinterpret_cast<uint4 *>(smem + p.nr_big * 2 * Kp);   // [2][RES2_SLOTS]: from the CTA above / from below
+    if (p.pair)
+        for (int i = tid; i < 2 * RES2_SLOTS; i += RES_NT) pslot[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < 16) arrive[tid] = 0u;
+    if (tid == 0) s_stop = 0;
+    __syncthreads();
+
+    // ---- load the strip -----------------------------------------------------------------------
+    DeepStrip<NR> s;
+    const bool idle = k >= K;
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < NR; ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int x = 2 * k + q, y = r0 + j;
+            s.v[j][q] = 0.0;
+            s.D[j][q] = 0.0;
+            if (!idle) {
+                const size_t i = (size_t)y * W + x;
+                s.D[j][q] = p.D[i];
+                s.v[j][q] = p.phi[i];
+                bad = bad || isnan(s.D[j][q]);
+                smem[(j * 2 + q) * Kp + 1 + k] = s.v[j][q];
+            }
+        }
+    constexpr int qa = (P0 + 1) & 1, qd = (P0 + NR) & 1;   // column parity of the colour-0 cell of the halo row above / below
+    s.hu = 0.0; s.hd = 0.0; s.Du = 0.0; s.Dd = 0.0;
+    if (!idle && has_up) {   // NaN anywhere in D is seen by its owner above; the halo cells only need their own D
+        const size_t i = (size_t)(r0 - 1) * W + 2 * k + qa;
+        s.hu = p.phi[i]; s.Du = p.D[i];
+    }
+    if (!idle && has_dn) {
+        const size_t i = (size_t)(r0 + NR) * W + 2 * k + qd;
+        s.hd = p.phi[i]; s.Dd = p.D[i];
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int x = 2 * k + q;
+        const int cx = (x != 0 ? 1 : 0) + (x != W - 1 ? 1 : 0);
+        const int cT = cx + (r0 != 0 ? 1 : 0) + 1, cB = cx + 1 + (r0 + NR != H ? 1 : 0), cM = cx + 2;
+        s.cT[q] = (double)cT; s.cM[q] = (double)cM; s.cB[q] = (double)cB;
+        s.wT[q] = wsel(p.w, cT); s.wM[q] = wsel(p.w, cM); s.wB[q] = wsel(p.w, cB);
+    }
+    const unsigned amask = __ballot_sync(0xffffffffu, !idle);
+    if (__syncthreads_or(bad ? 1 : 0)) {   // the masked neighbour rule is the other kernel's business: void the launch
+        if (tid == 0) atomicExch(err, RES_ERR_UNSUPPORTED);
+        if (p.pair) {
+            cooperative_groups::this_cluster().sync();
+            cooperative_groups::this_cluster().sync();
+        }
+        return;
+    }
+
+    uint4 *ll_up = has_up ? p.ll + ((size_t)(cta - 1) * 2 + 1) * RES2_SLOTS : nullptr;
+    uint4 *ll_dn = has_dn ? p.ll + ((size_t)(cta + 1) * 2 + 0) * RES2_SLOTS : nullptr;
+    const uint4 *in_top = p.ll + ((size_t)cta * 2 + 0) * RES2_SLOTS;
+    const uint4 *in_bot = p.ll + ((size_t)cta * 2 + 1) * RES2_SLOTS;
+    if (p.pair) {
+        cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+        const int rank = cta % p.pair;
+        if (rank != 0) { ll_up = cl.map_shared_rank(pslot + RES2_SLOTS, rank - 1); in_top = pslot; }
+        if (rank != p.pair - 1 && has_dn) { ll_dn = cl.map_shared_rank(pslot, rank + 1); in_bot = pslot + RES2_SLOTS; }
+    }
+    double *smk = smem + 1 + k;
+    // the colour-1 cell left / right of the halo cell that belongs to another thread: lane +-1, or -- for the first /
+    // last lane of a warp -- that thread's slot polled directly
+    const int keu = (qa == 0) ? k - 1 : k + 1, ked = (qd == 0) ? k - 1 : k + 1;
+    const bool nbu_ok = keu >= 0 && keu < K, nbd_ok = ked >= 0 && ked < K;
+    const bool edge_u = has_up && nbu_ok && lane == ((qa == 0) ? 0 : 31);
+    const bool edge_d = has_dn && nbd_ok && lane == ((qd == 0) ? 0 : 31);
+    __syncthreads();
+    if (p.pair) cooperative_groups::this_cluster().sync();
+
+    const int max_it = p.max_it;
+    int sweep = 0, conv_at = 0;
+    bool dead = false;   // this thread has seen the launch declared void
+    for (;; ++sweep) {
+        double lmax = 0.0;
+        unsigned long long pend = 0ull;
+        const int e = sweep - p.lag;
+        int errv = 0;
+        if (tid == 0) {
+            if (e >= 0) pend = *((const volatile unsigned long long *)(p.g_slot + e));
+            errv = *((volatile int *)err);
+        }
+        if (!idle) {
+            const bool first = sweep == 0;
+            const unsigned seq = (unsigned)sweep;             // the message consumed now was sent after sweep-1
+            const int bin = ((sweep + 1) & 1) * 2 * RES_NT + k;
+            // ---- colour 0 --------------------------------------------------------------------------
+            uint4 ru1 = make_uint4(0, 0, 0, 0), ru2 = ru1, rue = ru1, rd1 = ru1, rd2 = ru1, rde = ru1;
+            if (!first) {
+                if (has_up) { ru1 = ll_issue(in_top + bin); ru2 = ll_issue(in_top + bin + RES_NT); if (edge_u) rue = ll_issue(in_top + bin + (keu - k)); }
+                if (has_dn) { rd1 = ll_issue(in_bot + bin); rd2 = ll_issue(in_bot + bin + RES_NT); if (edge_d) rde = ll_issue(in_bot + bin + (ked - k)); }
+            }
+            deep_rows<NR, P0, EDGE, 0, 1, NR - 1>(s, smk, 0.0, 0.0, lmax);
+            double m1u = 0.0, m2u = 0.0, nbu = 0.0, m1d = 0.0, m2d = 0.0, nbd = 0.0;
+            if (first) {   // the halo rows of the first sweep come from the input field (untouched until every CTA is done)
+                if (has_up) {
+                    const double *row = p.phi + (size_t)(r0 - 1) * W;
+                    m1u = row[2 * k + (qa ^ 1)]; m2u = row[2 * k + qa - W];
+                    if (nbu_ok) nbu = row[2 * keu + (qa ^ 1)];
+                }
+                if (has_dn) {
+                    const double *row = p.phi + (size_t)(r0 + NR) * W;
+                    m1d = row[2 * k + (qd ^ 1)]; m2d = row[2 * k + qd + W];
+                    if (nbd_ok) nbd = row[2 * ked + (qd ^ 1)];
+                }
+            } else {
+                if (has_up) {
+                    m1u = ll_consume(ru1, in_top + bin, seq, err, dead);
+                    m2u = ll_consume(ru2, in_top + bin + RES_NT, seq, err, dead);
+                    nbu = (qa == 0) ? __shfl_up_sync(amask, m1u, 1) : __shfl_down_sync(amask, m1u, 1);
+                    if (edge_u) nbu = ll_consume(rue, in_top + bin + (keu - k), seq, err, dead);
+                    if (!nbu_ok) nbu = 0.0;
+                }
+                if (has_dn) {
+                    m1d = ll_consume(rd1, in_bot + bin, seq, err, dead);
+                    m2d = ll_consume(rd2, in_bot + bin + RES_NT, seq, err, dead);
+                    nbd = (qd == 0) ? __shfl_up_sync(amask, m1d, 1) : __shfl_down_sync(amask, m1d, 1);
+                    if (edge_d) nbd = ll_consume(rde, in_bot + bin + (ked - k), seq, err, dead);
+                    if (!nbd_ok) nbd = 0.0;
+                }
+            }
+            {
+                double halo_max = 0.0;   // the owner of a halo cell counts its update
+                const double nb0 = deep_nb<P0, 0, 0>(smk), nbl = deep_nb<P0, 0, NR - 1>(smk);
+                if (has_up)
+                    s.hu = sor_cell(s.hu, (qa == 0) ? nbu : m1u, m2u, (qa == 0) ? m1u : nbu, s.v[0][qa], s.cM[qa], s.wM[qa], s.Du, halo_max);
+                if (has_dn)
+                    s.hd = sor_cell(s.hd, (qd == 0) ? nbd : m1d, s.v[NR - 1][qd], (qd == 0) ? m1d : nbd, m2d, s.cM[qd], s.wM[qd], s.Dd, halo_max);
+                deep_cell<NR, P0, EDGE, 0, 0>(s, nb0, m1u, m1d, lmax);
+                deep_cell<NR, P0, EDGE, 0, NR - 1>(s, nbl, m1u, m1d, lmax);
+                smk[(0 * 2 + (P0 & 1)) * Kp] = s.v[0][P0 & 1];
+                smk[((NR - 1) * 2 + ((P0 + NR - 1) & 1)) * Kp] = s.v[NR - 1][(P0 + NR - 1) & 1];
+            }
+        }
+        {
+            const int wp = tid >> 5;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + (wp & ~1)) : "memory");
+            if (wp >= 1 && wp <= RES_NT / 32 - 2) asm volatile("bar.sync %0, 64;" ::"r"((wp & 1) ? 1 + wp : wp) : "memory");
+        }
+        if (!idle) {
+            // ---- colour 1: the rows the neighbours wait for first ------------------------------------
+            const int bout = (sweep & 1) * 2 * RES_NT + k;
+            const unsigned seq_out = (unsigned)sweep + 1u;
+            constexpr int TOP = NR < 2 ? NR : 2;                    // rows [0, TOP) and [BOT, NR) are sent
+            constexpr int BOT = (NR - 2 > TOP) ? NR - 2 : TOP;
+            deep_rows<NR, P0, EDGE, 1, 0, TOP>(s, smk, s.hu, s.hd, lmax);
+            deep_rows<NR, P0, EDGE, 1, BOT, NR>(s, smk, s.hu, s.hd, lmax);
+            if (ll_up) {
+                ll_store(ll_up + bout, s.v[0][(P0 + 1) & 1], seq_out);
+                ll_store(ll_up + bout + RES_NT, s.v[1][P0 & 1], seq_out);
+            }
+            if (ll_dn) {
+                ll_store(ll_dn + bout, s.v[NR - 1][(P0 + NR) & 1], seq_out);
+                ll_store(ll_dn + bout + RES_NT, s.v[NR - 2][(P0 + NR - 1) & 1], seq_out);
+            }
+            deep_rows<NR, P0, EDGE, 1, TOP, BOT>(s, smk, s.hu, s.hd, lmax);
+        }
+        if (tid == 0) {   // convergence duty: the verdict on sweep e = sweep - lag (as in res_body)
+            if (e >= 0 && conv_at == 0 && !errv) {
+                unsigned spins = 0u;
+                while ((unsigned)pend != (unsigned)p.P) {
+                    pend = *((const volatile unsigned long long *)(p.g_slot + e));
+                    if (res_give_up(spins, err)) { errv = 1; break; }
+                }
+                if (!errv && (pend >> 32) == 0ull) conv_at = e + 1;
+            }
+            if ((conv_at == e + 1 && e >= 0) || (errv && *((volatile int *)&s_stop) == 0))
+                *((volatile int *)&s_stop) = sweep + 1 + RES_STOP_AHEAD;
+        }
+        {
+            const int wp = tid >> 5;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + (wp & ~1)) : "memory");
+            if (wp >= 1 && wp <= RES_NT / 32 - 2) asm volatile("bar.sync %0, 64;" ::"r"((wp & 1) ? 1 + wp : wp) : "memory");
+        }
+        {
+            const bool wany = __any_sync(0xffffffffu, lmax >= p.tol);
+            if (!wany || sweep + p.lag + 3 >= max_it) {
+                const double wm = warp_max(lmax);
+                if ((tid & 31) == 0 && wm > 0.0) atomicMax(p.g_max + sweep, (unsigned long long)__double_as_longlong(wm));
+            }
+            if ((tid & 31) == 0) {
+                const unsigned add = 1u | (wany ? 0x10000u : 0u);
+                const unsigned old = atomicAdd(&arrive[sweep & 15], add);
+                if ((old & 0xffffu) == RES_NT / 32 - 1) {
+                    arrive[sweep & 15] = 0u;
+                    atomicAdd(p.g_slot + sweep, 1ull | (((old + add) >> 16) ? (1ull << 32) : 0ull));
+                }
+            }
+        }
+        if (*((volatile int *)&s_stop) == sweep + 1 || sweep + 1 >= max_it) break;
+    }
+
+    if (p.pair) cooperative_groups::this_cluster().sync();
+    if (tid == 0) {
+        int ok = *((volatile int *)err) == 0;
+        if (ok) {
+            atomicAdd(&p.state->done, 1);
+            unsigned spins = 0u;
+            while (*((volatile int *)&p.state->done) != p.P)
+                if (res_give_up(spins, err)) { ok = 0; break; }
+        }
+        s_stop = ok ? -1 : -2;
+    }
+    __syncthreads();
+    if (s_stop != -1) return;
+    if (!idle) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) p.phi[(size_t)(r0 + j) * W + 2 * k + q] = s.v[j][q];
+    }
+    if (tid == 0 && cta == 0) {
+        p.state->sweeps = sweep + 1;
+        p.state->converged_at = conv_at;
+    }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(RES_NT, 1) sor_resident_deep_kernel(const __grid_constant__ ResParams p) {
+    const int c = (int)blockIdx.x;
+    const bool edge = c == 0 || c + 1 == p.P;
+    if (c >= p.P) {
+        cooperative_groups::this_cluster().sync();
+        cooperative_groups::this_cluster().sync();
+        return;
+    }
+    const bool big = c < p.n_big;
+    const int r0 = big ? c * NR : p.n_big * NR + (c - p.n_big) * (NR - 1);
+    if (big) {
+        if (edge) { if (r0 & 1) deep_body<NR, 1, true>(p, r0); else deep_body<NR, 0, true>(p, r0); }
+        else      { if (r0 & 1) deep_body<NR, 1, false>(p, r0); else deep_body<NR, 0, false>(p, r0); }
+    } else {
+        if (edge) { if (r0 & 1) deep_body<NR - 1, 1, true>(p, r0); else deep_body<NR - 1, 0, true>(p, r0); }
+        else      { if (r0 & 1) deep_body<NR - 1, 1, false>(p, r0); else deep_body<NR - 1, 0, false>(p, r0); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-int resident_slots() { return RES_SLOTS; }
+int resident_slots() { return RES2_SLOTS; }
 
 int resident_plan(pcd_solver *s) {
     const int W = s->W, H = s->H;
@@ -442,14 +795,18 @@ int resident_plan(pcd_solver *s) {
     const int Kp = RES_KP;
     s->res_ctas = P;
     s->res_rows_per_cta = pick;
-    s->res_smem = (size_t)pick * 2 * Kp * sizeof(double) + (size_t)2 * RES_SLOTS * sizeof(uint4);  // + slots of the links inside a cluster
+    s->res_smem = (size_t)pick * 2 * Kp * sizeof(double) + (size_t)2 * RES2_SLOTS * sizeof(uint4);  // + slots of the links inside a cluster
     s->res_threads = RES_NT;
     return 1;
 }
 
 template <int NR>
-static int launch_resident(pcd_solver *s, ResParams &prm) {
-    PCD_CUDA(cudaFuncSetAttribute(sor_resident_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->res_smem));
+static int launch_resident(pcd_solver *s, ResParams &prm, bool deep) {
+    void (*kernel)(const ResParams) = sor_resident_kernel<NR>;
+    if constexpr (NR >= 3) {
+        if (deep) kernel = sor_resident_deep_kernel<NR>;
+    }
+    PCD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->res_smem));
     // preferred: clusters of two CTAs (one TPC each); the link inside a pair then runs over DSMEM and only every other
     // link crosses L2.  This launch carries the cluster attribute only (cluster + cooperative is refused under the
     // profiler): with one CTA per SM and at most one CTA per SM in the grid all pairs are resident on an idle device,
@@ -467,13 +824,13 @@ static int launch_resident(pcd_solver *s, ResParams &prm) {
         cfg.attrs = at; cfg.numAttrs = 1;
         if (s->res_pairs == 0) {   // decide once per solver
             int n = 0;
-            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, sor_resident_kernel<NR>, &cfg);
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
             s->res_pairs = (e == cudaSuccess && n * cs >= grid) ? 1 : -1;
             if (e != cudaSuccess) cudaGetLastError();
         }
         if (s->res_pairs == 1) {
             prm.pair = cs;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, sor_resident_kernel<NR>, prm);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, prm);
             if (e == cudaSuccess) { PCD_LAUNCHED(); return PCD_OK; }
             cudaGetLastError();
             s->res_pairs = -1;
@@ -481,7 +838,7 @@ static int launch_resident(pcd_solver *s, ResParams &prm) {
     }
     prm.pair = 0;
     void *args[] = {&prm};
-    PCD_CUDA(cudaLaunchCooperativeKernel((void *)sor_resident_kernel<NR>, dim3(s->res_ctas), dim3(RES_NT), args,
+    PCD_CUDA(cudaLaunchCooperativeKernel((void *)kernel, dim3(s->res_ctas), dim3(RES_NT), args,
                                          s->res_smem, s->stream));
     PCD_LAUNCHED();
     return PCD_OK;
@@ -495,11 +852,14 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
     double last = 0.0;
     unsigned long long *g_max = s->sweep_max;
     unsigned long long *g_slot = s->sweep_max + s->ring;
+    // one exchange per sweep (deep halos) wherever its preconditions hold; a NaN in D is only found by the kernel itself
+    const bool no_deep = getenv("PCD_RES_NO_DEEP") != nullptr;   // read per solve: the tests compare both kernels
+    bool deep = !no_deep && W % 2 == 0 && s->res_rows_per_cta >= 3;
     while (done < max_it && !conv) {
         const int k = max_it - done < RES_MAX_SWEEPS_PER_LAUNCH ? max_it - done : RES_MAX_SWEEPS_PER_LAUNCH;
         PCD_CUDA(cudaMemsetAsync(g_max, 0, sizeof(unsigned long long) * (size_t)k, s->stream));
         PCD_CUDA(cudaMemsetAsync(g_slot, 0, sizeof(unsigned long long) * (size_t)k, s->stream));
-        PCD_CUDA(cudaMemsetAsync(s->halo, 0, (size_t)P * 2 * RES_SLOTS * sizeof(uint4), s->stream));
+        PCD_CUDA(cudaMemsetAsync(s->halo, 0, (size_t)P * 2 * RES2_SLOTS * sizeof(uint4), s->stream));
         PCD_CUDA(cudaMemsetAsync(s->res_state, 0, sizeof(ResState), s->stream));
         ResParams prm;
         prm.phi = phi; prm.D = D; prm.W = W; prm.H = H; prm.K = (W + 1) / 2;
@@ -509,13 +869,13 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
         int rc;
         PCD_CUDA(cudaEventRecord(s->evk0, s->stream));
         switch (s->res_rows_per_cta) {
-            case 1: rc = launch_resident<1>(s, prm); break;
-            case 2: rc = launch_resident<2>(s, prm); break;
-            case 3: rc = launch_resident<3>(s, prm); break;
-            case 4: rc = launch_resident<4>(s, prm); break;
-            case 5: rc = launch_resident<5>(s, prm); break;
-            case 6: rc = launch_resident<6>(s, prm); break;
-            default: rc = launch_resident<7>(s, prm); break;
+            case 1: rc = launch_resident<1>(s, prm, deep); break;
+            case 2: rc = launch_resident<2>(s, prm, deep); break;
+            case 3: rc = launch_resident<3>(s, prm, deep); break;
+            case 4: rc = launch_resident<4>(s, prm, deep); break;
+            case 5: rc = launch_resident<5>(s, prm, deep); break;
+            case 6: rc = launch_resident<6>(s, prm, deep); break;
+            default: rc = launch_resident<7>(s, prm, deep); break;
         }
         PCD_TRY(rc);
         PCD_CUDA(cudaEventRecord(s->evk1, s->stream));
@@ -523,6 +883,7 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
         PCD_CUDA(cudaMemcpyAsync(s->h_res_state, s->res_state, sizeof(ResState), cudaMemcpyDeviceToHost, s->stream));
         PCD_CUDA(cudaStreamSynchronize(s->stream));
         const ResState st = *(ResState *)s->h_res_state;
+        if (st.error == RES_ERR_UNSUPPORTED && deep) { deep = false; continue; }   // NaN holes: phi is untouched
         if (st.error) {  // a CTA waited in vain: phi is untouched
             if (s->res_pairs == 1) { s->res_pairs = -1; continue; }   // once more, cooperatively
             set_error("resident K-SOR kernel: a CTA gave up waiting for its neighbour");
@@ -546,6 +907,7 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
         }
         if (conv_local) conv = done + conv_local;
         done += st.sweeps;
+        s->res_exchange = deep ? 2 : 1;
     }
     info->sweeps = done;
     info->converged_at = conv;

@@ -265,3 +265,63 @@ def test_check_lag_is_clamped(pcd, port):
     s.upload(D, np.zeros_like(D))
     assert s.run(100000, 1e-7)["converged_at"] > 0
     s.close()
+
+
+@pytest.mark.parametrize("shape", [(400, 400), (444, 64), (298, 36), (297, 66), (600, 202), (740, 6), (1036, 1024), (1024, 1024),
+                                   (512, 130), (900, 1000)])
+def test_resident_deep_halo_kernel_bit_exact(pcd, port, shape, monkeypatch):
+    """The resident kernel with ONE neighbour exchange per sweep (redundant update of the colour-0 cells of the rows just
+    outside a slab, double-buffered messages, lane shuffles + edge-lane polls for the halo row's left/right cells):
+    pinned to the oracle after 1, 2, 3, 10 and 41 sweeps, to the exchange-per-phase kernel after a converged run, on
+    shapes with slabs of 2..7 rows, one to 512 column pairs, partly filled warps and single-lane warps."""
+    H, W = shape
+    rng = np.random.RandomState(7 * H + W)
+    D = rng.standard_normal((H, W))
+    D -= D.mean()
+    phi0 = rng.standard_normal((H, W))
+    s = pcd.Solver(W, H, 0, pcd.SOLVER_RESIDENT)
+    for n in (1, 2, 3, 10, 41):
+        s.upload(D, phi0)
+        info = s.run(n, 0.0)
+        assert s.resident_exchange == 2 and info["launches"] == 1
+        want, k, conv, last = port.poisson_rb(D, phi0, n, 0.0)
+        got = s.download()
+        assert np.array_equal(got, want), (shape, n, np.abs(got - want).max())
+        assert info["sweeps"] == n and info["last_max_update"] == last
+    z = np.zeros_like(D)
+    D2 = D * 1e-3
+    s.upload(D2, z)
+    deep = s.run(100000, 1e-6)
+    f_deep = s.download()
+    assert s.resident_exchange == 2 and 0 < deep["converged_at"] <= deep["sweeps"] <= deep["converged_at"] + 64
+    monkeypatch.setenv("PCD_RES_NO_DEEP", "1")
+    s.upload(D2, z)
+    classic = s.run(100000, 1e-6)
+    assert s.resident_exchange == 1
+    assert classic["converged_at"] == deep["converged_at"] and classic["sweeps"] == deep["sweeps"]
+    assert np.array_equal(s.download(), f_deep)
+    assert classic["last_max_update"] == deep["last_max_update"]
+    s.close()
+
+
+def test_resident_deep_halo_kernel_hands_nan_holes_back(pcd, port):
+    """NaN holes need the masked neighbour rule: the deep-halo kernel finds them while loading, voids its launch without
+    touching the field, and the exchange-per-phase kernel runs instead."""
+    H, W = 400, 400
+    rng = np.random.RandomState(5)
+    D = rng.standard_normal((H, W))
+    D[100:140, 200:260] = np.nan
+    D[399, 399] = np.nan
+    phi0 = rng.standard_normal((H, W))
+    s = pcd.Solver(W, H, 0, pcd.SOLVER_RESIDENT)
+    s.upload(D, phi0)
+    info = s.run(25, 0.0)
+    assert s.resident_exchange == 1 and info["launches"] == 2 and info["sweeps"] == 25
+    want = port.poisson_rb(D, phi0, 25, 0.0)[0]
+    assert np.array_equal(s.download(), want, equal_nan=True)
+    D[np.isnan(D)] = 0.5
+    s.upload(D, phi0)
+    info = s.run(25, 0.0)
+    assert s.resident_exchange == 2 and info["launches"] == 1
+    assert np.array_equal(s.download(), port.poisson_rb(D, phi0, 25, 0.0)[0])
+    s.close()

@@ -1,3 +1,4 @@
 #!/bin/bash
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_pipeline.py -m gpu -q -k "c5_stages or c4_first or height_tol" 2>&1 | tail -12 | cut -c1-300
+timeout 600 python -m pytest tests/test_gpu_solver.py -m gpu -q -x -k "deep_halo or production_sizes or resident_1024" 2>&1 | tail -15 | cut -c1-400
+timeout 300 python tools/res_time.py 1024x1024 1000x1000 400x400 1024x512 1024x896 2>&1 | tail -8
