@@ -322,7 +322,7 @@ class DesignRunner:
             info = cd.last_solve_info()
             recs.append({"ms": ms, "step": step, "sweeps": info["sweeps"], "kernel_ms": info["kernel_ms"],
                          "solve_launches": info["launches"], "launches": P.launch_count() - l0, "path": info["path"],
-                         "it": self.it_in_design})
+                         "exchange": cd.resident_exchange, "it": self.it_in_design})
             self.after_step(step, more=k + 1 < n)
         return recs
 
@@ -549,7 +549,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     us_per_sweep = kernel_ms * 1e3 / sweeps if sweeps else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (traffic["dram_bytes_per_launch"] if path == "resident" else wave_traffic(traffic, W * H // (world if distributed else 1), sweeps / max(solve_launches, 1))) if traffic else None,
-                "kernel": {"resident": "sor_resident_kernel", "tiled": "sor_wave_kernel", "dct": "dct_gemm_kernel"}.get(path, "sor_colour_kernel"),
+                "kernel": {"resident": "sor_resident_deep_kernel" if recs[-1].get("exchange") == 2 else "sor_resident_kernel", "tiled": "sor_wave_kernel", "dct": "dct_gemm_kernel"}.get(path, "sor_colour_kernel"),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / max(solve_launches, 1) / (world if distributed else 1),
                 "sweeps_per_launch": sweeps / max(solve_launches, 1),
@@ -560,9 +560,15 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                          "of both fields, far below the algorithmic bytes, so HBM is NOT this kernel's roof (see on_chip)" if path == "resident" else
                          "temporal blocking: 2 sweeps per HBM pass (12 B/cell/sweep of real traffic), one persistent launch per block of passes")}
     if path == "resident" and (W, H) == (1024, 1024) and us_per_sweep:
-        roofline["on_chip"] = dict(RESIDENT_FLOORS_1024, us_per_sweep=us_per_sweep,
-                                   frac_of_exchange_floor=RESIDENT_FLOORS_1024["exchange_floor_us_per_sweep"] / us_per_sweep,
-                                   frac_of_fp64_floor=RESIDENT_FLOORS_1024["fp64_floor_us_per_sweep"] / us_per_sweep)
+        # the deep-halo kernel exchanges once per sweep (same message volume, half the round trips): its chain floor is ONE
+        # chain2 exchange per sweep, and its fp64 floor carries the redundantly updated colour-0 halo cells (8/7 at 7 rows/CTA)
+        deep = recs[-1].get("exchange") == 2
+        xf = RESIDENT_FLOORS_1024["exchange_floor_us_per_sweep"] * (0.5 if deep else 1.0)
+        ff = RESIDENT_FLOORS_1024["fp64_floor_us_per_sweep"] * (8.0 / 7.0 if deep else 1.0)
+        roofline["on_chip"] = {"exchange_floor_us_per_sweep": xf, "fp64_floor_us_per_sweep": ff,
+                               "exchanges_per_sweep": 1 if deep else 2, "source": RESIDENT_FLOORS_1024["source"],
+                               "us_per_sweep": us_per_sweep, "frac_of_exchange_floor": xf / us_per_sweep,
+                               "frac_of_fp64_floor": ff / us_per_sweep}
     # the whole-design figure: a complete design inside the timed window if there is one, else the warm-up design
     src, src_name = (recs[:n_it], "timed window") if steps >= n_it else (warm[:n_it], "warm-up design (first launches included)")
     d_ms = sum(r["ms"] for r in src)

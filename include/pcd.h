@@ -118,6 +118,8 @@ int pcd_get_field(pcd_ctx *ctx, int field, double *dst);
 int pcd_set_field(pcd_ctx *ctx, int field, const double *src);            /* members are public in the reference */
 int pcd_inverted_transport_map(pcd_ctx *ctx, double *out_x, double *out_y); /* Mesh::calculate_inverted_transport_map src/mesh.cpp:348-409 */
 int pcd_last_solve_info(const pcd_ctx *ctx, pcd_solve_info *info);
+/* resident kernel of the context's last built-in solve (see pcd_solver_resident_exchange): 0 none, 1 per phase, 2 per sweep */
+int pcd_resident_exchange(const pcd_ctx *ctx);
 /* totals over every solve since the last reset: sweeps, launches, kernel_ms, device_ms are summed */
 int pcd_solve_totals(pcd_ctx *ctx, pcd_solve_info *totals, int reset);
 /* device timing on the context's own stream (torch.cuda.Event only sees torch's stream): slots 0..7 */

@@ -94,6 +94,7 @@ ABI = [
     ("pcd_solver_run", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.POINTER(pcd_solve_info)]),
     ("pcd_solver_path_used", C.c_int, [C.c_void_p]),
     ("pcd_solver_resident_exchange", C.c_int, [C.c_void_p]),
+    ("pcd_resident_exchange", C.c_int, [C.c_void_p]),
     ("pcd_slab_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     ("pcd_slab_destroy", None, [C.c_void_p]),
     ("pcd_slab_device_ptrs", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
@@ -331,6 +332,11 @@ class CausticDesign:
         info = pcd_solve_info()
         _check(lib().pcd_last_solve_info(self._h, C.byref(info)))
         return info.as_dict()
+
+    @property
+    def resident_exchange(self) -> int:
+        """Resident kernel of the last built-in solve: 0 none, 1 one exchange per colour phase, 2 one per sweep."""
+        return lib().pcd_resident_exchange(self._h)
 
     def solve_totals(self, reset: bool = False) -> dict:
         info = pcd_solve_info()

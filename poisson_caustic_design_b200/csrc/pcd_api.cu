@@ -312,6 +312,8 @@ int pcd_last_solve_info(const pcd_ctx *ctx, pcd_solve_info *info) {
     return PCD_OK;
 }
 
+int pcd_resident_exchange(const pcd_ctx *ctx) { return ctx ? ctx->solver.res_exchange : -1; }
+
 int pcd_solve_totals(pcd_ctx *ctx, pcd_solve_info *totals, int reset) {
     if (!ctx) { set_error("null argument"); return PCD_ERR_INVALID; }
     if (totals) *totals = ctx->totals;
