@@ -456,6 +456,29 @@ __global__ void __launch_bounds__(RES_NT, 1) sor_resident_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------
 constexpr int RES2_SLOTS = 4 * RES_NT;   // [sweep parity][0: row next to the receiver, 1: the row behind it][RES_NT]
 constexpr int RES_ERR_UNSUPPORTED = 2;
+// Build switches of the deep-halo kernel (all bit-identical; the defaults are the measured winners, tools/experiments):
+//   PCD_DEEP_DSMEM    D lives in shared memory instead of registers (28 registers less at 7 rows: no spills, no
+//                     re-materialised neighbour counts, room to overlap the cells' dependency chains)
+//   PCD_DEEP_FASTPOLL the six messages of a sweep are tested with ONE branch; the per-message poll loop is the slow path
+//   PCD_DEEP_PRESEND  the halo rows of the first sweep travel as messages too (sent before the loop from the loaded
+//                     strip), so the loop has no first-sweep case
+#ifndef PCD_DEEP_DSMEM
+#define PCD_DEEP_DSMEM 1
+#endif
+#ifndef PCD_DEEP_FASTPOLL
+#define PCD_DEEP_FASTPOLL 1
+#endif
+#ifndef PCD_DEEP_PRESEND
+#define PCD_DEEP_PRESEND 1
+#endif
+#ifndef PCD_DEEP_POLL_AFTER
+#define PCD_DEEP_POLL_AFTER 0   // interior rows of colour 0 updated before the first poll of a sweep is issued
+#endif
+constexpr bool DEEP_DSMEM = PCD_DEEP_DSMEM != 0, DEEP_FASTPOLL = PCD_DEEP_FASTPOLL != 0, DEEP_PRESEND = PCD_DEEP_PRESEND != 0;
+
+__device__ __forceinline__ double ll_value(const uint4 r) {
+    return __longlong_as_double((long long)(((unsigned long long)r.z << 32) | r.x));
+}
 
 template <int A, int B, class F>
 __device__ __forceinline__ void static_rows(F &&f) {
@@ -476,14 +499,14 @@ __device__ __forceinline__ double sor_cell(const double val, const double l, con
 
 template <int NR>
 struct DeepStrip {
-    double v[NR][2], D[NR][2];
+    double v[NR][2], D[DEEP_DSMEM ? 1 : NR][2];   // D: registers, or shared memory (DEEP_DSMEM)
     double cM[2], wM[2], cT[2], wT[2], cB[2], wB[2];   // T / B only live in the first / last slab
     double hu, hd, Du, Dd;   // colour-0 cell of the halo rows r0-1 / r0+NR in this thread's column pair, and its D
 };
 
 // update of the colour-C cell of slab row J (P0 = column parity of the colour-0 cell of row 0)
 template <int NR, int P0, bool EDGE, int C, int J>
-__device__ __forceinline__ void deep_cell(DeepStrip<NR> &s, const double nb, const double upv, const double dnv, double &lmax) {
+__device__ __forceinline__ void deep_cell(DeepStrip<NR> &s, const double nb, const double Dv, const double upv, const double dnv, double &lmax) {
     constexpr int q = (P0 + C + J) & 1;
     const double own = s.v[J][q ^ 1];
     const double l = (q == 0) ? nb : own, r = (q == 0) ? own : nb;
@@ -491,7 +514,15 @@ __device__ __forceinline__ void deep_cell(DeepStrip<NR> &s, const double nb, con
     const double d = (J == NR - 1) ? dnv : s.v[(J == NR - 1) ? J : J + 1][q];
     const double cnt = (EDGE && J == 0) ? s.cT[q] : ((EDGE && J == NR - 1) ? s.cB[q] : s.cM[q]);
     const double wv = (EDGE && J == 0) ? s.wT[q] : ((EDGE && J == NR - 1) ? s.wB[q] : s.wM[q]);
-    s.v[J][q] = sor_cell(s.v[J][q], l, u, r, d, cnt, wv, s.D[J][q], lmax);
+    s.v[J][q] = sor_cell(s.v[J][q], l, u, r, d, cnt, wv, Dv, lmax);
+}
+
+// D of the colour-C cell of row J: a register, or this thread's own shared-memory word (unit stride over the warp)
+template <int NR, int P0, int C, int J>
+__device__ __forceinline__ double deep_D(const DeepStrip<NR> &s, const double *__restrict__ smD) {
+    constexpr int q = (P0 + C + J) & 1;
+    if constexpr (DEEP_DSMEM) return smD[(J * 2 + q) * RES_KP];
+    else return s.D[J][q];
 }
 
 template <int P0, int C, int J>
@@ -502,16 +533,18 @@ __device__ __forceinline__ double deep_nb(const double *__restrict__ smk) {
 
 // rows [A, B) of colour C: all shared-memory reads, then the arithmetic, then the writes
 template <int NR, int P0, bool EDGE, int C, int A, int B>
-__device__ __forceinline__ void deep_rows(DeepStrip<NR> &s, double *__restrict__ smk, const double upv, const double dnv, double &lmax) {
+__device__ __forceinline__ void deep_rows(DeepStrip<NR> &s, double *__restrict__ smk, const double *__restrict__ smD,
+                                          const double upv, const double dnv, double &lmax) {
     if constexpr (A < B) {
-        double nb[B - A];
+        double nb[B - A], dv[B - A];
         static_rows<A, B>([&](auto Jc) {
             constexpr int J = decltype(Jc)::value;
             nb[J - A] = deep_nb<P0, C, J>(smk);
+            dv[J - A] = deep_D<NR, P0, C, J>(s, smD);
         });
         static_rows<A, B>([&](auto Jc) {
             constexpr int J = decltype(Jc)::value;
-            deep_cell<NR, P0, EDGE, C, J>(s, nb[J - A], upv, dnv, lmax);
+            deep_cell<NR, P0, EDGE, C, J>(s, nb[J - A], dv[J - A], upv, dnv, lmax);
         });
         static_rows<A, B>([&](auto Jc) {
             constexpr int J = decltype(Jc)::value, q = (P0 + C + J) & 1;
@@ -523,7 +556,7 @@ __device__ __forceinline__ void deep_rows(DeepStrip<NR> &s, double *__restrict__
 template <int NR, int P0, bool EDGE>
 __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
     static_assert(NR >= 2, "deep halos need two rows per slab");
-    extern __shared__ double smem[];  // [NR][2][Kp] as in res_body, then the slots of the links inside a cluster
+    extern __shared__ double smem[];  // phi [nr_big][2][Kp] as in res_body, D likewise (DEEP_DSMEM), then the slots of the links inside a cluster
     __shared__ unsigned arrive[16];
     __shared__ int s_stop;
 
@@ -532,9 +565,11 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
     constexpr int Kp = RES_KP;
     const bool has_up = !EDGE || cta > 0, has_dn = !EDGE || cta + 1 < p.P;
     int *const err = &p.state->error;
+    constexpr int PLANES = DEEP_DSMEM ? 2 : 1;
 
     for (int i = tid; i < NR * 2 * Kp; i += RES_NT) smem[i] = 0.0;
-    uint4 *pslot = reinterpret_cast<uint4 *>(smem + p.nr_big * 2 * Kp);   // [2][RES2_SLOTS]: from the CTA above / from below
+    uint4 *pslot = reinterpret_cast<uint4 *>(smem + p.nr_big * 2 * Kp * PLANES);   // [2][RES2_SLOTS]: from the CTA above / from below
+    double *const smD = smem + p.nr_big * 2 * Kp + 1 + k;   // D of (row j, parity q) of this thread at smD[(j*2+q)*Kp]
     if (p.pair)
         for (int i = tid; i < 2 * RES2_SLOTS; i += RES_NT) pslot[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid < 16) arrive[tid] = 0u;
@@ -551,12 +586,14 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
         for (int q = 0; q < 2; ++q) {
             const int x = 2 * k + q, y = r0 + j;
             s.v[j][q] = 0.0;
-            s.D[j][q] = 0.0;
+            if constexpr (!DEEP_DSMEM) s.D[j][q] = 0.0;
             if (!idle) {
                 const size_t i = (size_t)y * W + x;
-                s.D[j][q] = p.D[i];
+                const double Dv = p.D[i];
+                if constexpr (DEEP_DSMEM) smD[(j * 2 + q) * Kp] = Dv;   // only ever read by this thread
+                else s.D[j][q] = Dv;
                 s.v[j][q] = p.phi[i];
-                bad = bad || isnan(s.D[j][q]);
+                bad = bad || isnan(Dv);
                 smem[(j * 2 + q) * Kp + 1 + k] = s.v[j][q];
             }
         }
@@ -608,6 +645,23 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
     __syncthreads();
     if (p.pair) cooperative_groups::this_cluster().sync();
 
+    // sequence number of the message consumed by sweep s: s (the halo rows of sweep 0 are read from the input field), or
+    // s + 1 when the first sweep's halo rows travel as messages as well (slots are zeroed by the host: 0 is never valid)
+    constexpr unsigned SEQ0 = DEEP_PRESEND ? 1u : 0u;
+    if constexpr (DEEP_PRESEND) {
+        if (!idle) {
+            const int b1 = 2 * RES_NT + k;   // the buffer sweep 0 reads: ((0 + 1) & 1)
+            if (ll_up) {
+                ll_store(ll_up + b1, s.v[0][(P0 + 1) & 1], SEQ0);
+                ll_store(ll_up + b1 + RES_NT, s.v[1][P0 & 1], SEQ0);
+            }
+            if (ll_dn) {
+                ll_store(ll_dn + b1, s.v[NR - 1][(P0 + NR) & 1], SEQ0);
+                ll_store(ll_dn + b1 + RES_NT, s.v[NR - 2][(P0 + NR - 1) & 1], SEQ0);
+            }
+        }
+    }
+
     const int max_it = p.max_it;
     int sweep = 0, conv_at = 0;
     bool dead = false;   // this thread has seen the launch declared void
@@ -621,53 +675,109 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
             errv = *((volatile int *)err);
         }
         if (!idle) {
-            const bool first = sweep == 0;
-            const unsigned seq = (unsigned)sweep;             // the message consumed now was sent after sweep-1
+            const bool first = !DEEP_PRESEND && sweep == 0;
+            const unsigned seq = (unsigned)sweep + SEQ0;      // the message consumed now was sent after sweep-1
             const int bin = ((sweep + 1) & 1) * 2 * RES_NT + k;
             // ---- colour 0 --------------------------------------------------------------------------
-            uint4 ru1 = make_uint4(0, 0, 0, 0), ru2 = ru1, rue = ru1, rd1 = ru1, rd2 = ru1, rde = ru1;
-            if (!first) {
-                if (has_up) { ru1 = ll_issue(in_top + bin); ru2 = ll_issue(in_top + bin + RES_NT); if (edge_u) rue = ll_issue(in_top + bin + (keu - k)); }
-                if (has_dn) { rd1 = ll_issue(in_bot + bin); rd2 = ll_issue(in_bot + bin + RES_NT); if (edge_d) rde = ll_issue(in_bot + bin + (ked - k)); }
-            }
-            deep_rows<NR, P0, EDGE, 0, 1, NR - 1>(s, smk, 0.0, 0.0, lmax);
             double m1u = 0.0, m2u = 0.0, nbu = 0.0, m1d = 0.0, m2d = 0.0, nbd = 0.0;
-            if (first) {   // the halo rows of the first sweep come from the input field (untouched until every CTA is done)
-                if (has_up) {
-                    const double *row = p.phi + (size_t)(r0 - 1) * W;
-                    m1u = row[2 * k + (qa ^ 1)]; m2u = row[2 * k + qa - W];
-                    if (nbu_ok) nbu = row[2 * keu + (qa ^ 1)];
+            if constexpr (DEEP_FASTPOLL) {
+                uint4 ru1 = make_uint4(0u, 0u, 0u, 0u), ru2 = ru1, rd1 = ru1, rd2 = ru1;
+                uint4 rue, rde;   // only the first / last lane of a warp has these (read under edge_u / edge_d alone)
+                // the first poll is issued after SPLIT - 1 of the interior rows: late enough to find the message, early
+                // enough for the rest of the interior to cover its latency
+                constexpr int SPLIT = (1 + PCD_DEEP_POLL_AFTER < NR - 1) ? 1 + PCD_DEEP_POLL_AFTER : (NR - 1 > 1 ? NR - 1 : 1);
+                deep_rows<NR, P0, EDGE, 0, 1, SPLIT>(s, smk, smD, 0.0, 0.0, lmax);
+                if (!first) {
+                    if (has_up) { ru1 = ll_issue(in_top + bin); ru2 = ll_issue(in_top + bin + RES_NT); if (edge_u) rue = ll_issue(in_top + bin + (keu - k)); }
+                    if (has_dn) { rd1 = ll_issue(in_bot + bin); rd2 = ll_issue(in_bot + bin + RES_NT); if (edge_d) rde = ll_issue(in_bot + bin + (ked - k)); }
                 }
-                if (has_dn) {
-                    const double *row = p.phi + (size_t)(r0 + NR) * W;
-                    m1d = row[2 * k + (qd ^ 1)]; m2d = row[2 * k + qd + W];
-                    if (nbd_ok) nbd = row[2 * ked + (qd ^ 1)];
+                deep_rows<NR, P0, EDGE, 0, SPLIT, NR - 1>(s, smk, smD, 0.0, 0.0, lmax);
+                if (first) {   // (!DEEP_PRESEND) the halo rows of the first sweep come from the input field
+                    if (has_up) {
+                        const double *row = p.phi + (size_t)(r0 - 1) * W;
+                        m1u = row[2 * k + (qa ^ 1)]; m2u = row[2 * k + qa - W];
+                        if (nbu_ok) nbu = row[2 * keu + (qa ^ 1)];
+                    }
+                    if (has_dn) {
+                        const double *row = p.phi + (size_t)(r0 + NR) * W;
+                        m1d = row[2 * k + (qd ^ 1)]; m2d = row[2 * k + qd + W];
+                        if (nbd_ok) nbd = row[2 * ked + (qd ^ 1)];
+                    }
+                } else {
+                    // ONE test for all messages of the sweep.  Whatever is still missing is then re-polled TOGETHER (all
+                    // loads in flight at once: a round of re-polls costs one L2 round trip, not one per message)
+                    unsigned spins = 0u;
+                    for (;;) {
+                        unsigned su1 = 0u, su2 = 0u, sue = 0u, sd1 = 0u, sd2 = 0u, sde = 0u;
+                        if (has_up) { su1 = (ru1.y ^ seq) | (ru1.w ^ seq); su2 = (ru2.y ^ seq) | (ru2.w ^ seq); if (edge_u) sue = (rue.y ^ seq) | (rue.w ^ seq); }
+                        if (has_dn) { sd1 = (rd1.y ^ seq) | (rd1.w ^ seq); sd2 = (rd2.y ^ seq) | (rd2.w ^ seq); if (edge_d) sde = (rde.y ^ seq) | (rde.w ^ seq); }
+                        if ((((su1 | su2) | sue) | ((sd1 | sd2) | sde)) == 0u || dead) break;
+                        if (su1) ru1 = ll_issue(in_top + bin);
+                        if (su2) ru2 = ll_issue(in_top + bin + RES_NT);
+                        if (sue) rue = ll_issue(in_top + bin + (keu - k));
+                        if (sd1) rd1 = ll_issue(in_bot + bin);
+                        if (sd2) rd2 = ll_issue(in_bot + bin + RES_NT);
+                        if (sde) rde = ll_issue(in_bot + bin + (ked - k));
+                        if (res_give_up(spins, err)) dead = true;
+                    }
+                    if (has_up) {
+                        m1u = ll_value(ru1); m2u = ll_value(ru2);
+                        nbu = (qa == 0) ? __shfl_up_sync(amask, m1u, 1) : __shfl_down_sync(amask, m1u, 1);
+                        if (edge_u) nbu = ll_value(rue);
+                        if (!nbu_ok) nbu = 0.0;
+                    }
+                    if (has_dn) {
+                        m1d = ll_value(rd1); m2d = ll_value(rd2);
+                        nbd = (qd == 0) ? __shfl_up_sync(amask, m1d, 1) : __shfl_down_sync(amask, m1d, 1);
+                        if (edge_d) nbd = ll_value(rde);
+                        if (!nbd_ok) nbd = 0.0;
+                    }
                 }
             } else {
-                if (has_up) {
-                    m1u = ll_consume(ru1, in_top + bin, seq, err, dead);
-                    m2u = ll_consume(ru2, in_top + bin + RES_NT, seq, err, dead);
-                    nbu = (qa == 0) ? __shfl_up_sync(amask, m1u, 1) : __shfl_down_sync(amask, m1u, 1);
-                    if (edge_u) nbu = ll_consume(rue, in_top + bin + (keu - k), seq, err, dead);
-                    if (!nbu_ok) nbu = 0.0;
+                uint4 ru1 = make_uint4(0, 0, 0, 0), ru2 = ru1, rue = ru1, rd1 = ru1, rd2 = ru1, rde = ru1;
+                if (!first) {
+                    if (has_up) { ru1 = ll_issue(in_top + bin); ru2 = ll_issue(in_top + bin + RES_NT); if (edge_u) rue = ll_issue(in_top + bin + (keu - k)); }
+                    if (has_dn) { rd1 = ll_issue(in_bot + bin); rd2 = ll_issue(in_bot + bin + RES_NT); if (edge_d) rde = ll_issue(in_bot + bin + (ked - k)); }
                 }
-                if (has_dn) {
-                    m1d = ll_consume(rd1, in_bot + bin, seq, err, dead);
-                    m2d = ll_consume(rd2, in_bot + bin + RES_NT, seq, err, dead);
-                    nbd = (qd == 0) ? __shfl_up_sync(amask, m1d, 1) : __shfl_down_sync(amask, m1d, 1);
-                    if (edge_d) nbd = ll_consume(rde, in_bot + bin + (ked - k), seq, err, dead);
-                    if (!nbd_ok) nbd = 0.0;
+                deep_rows<NR, P0, EDGE, 0, 1, NR - 1>(s, smk, smD, 0.0, 0.0, lmax);
+                if (first) {   // the halo rows of the first sweep come from the input field (untouched until every CTA is done)
+                    if (has_up) {
+                        const double *row = p.phi + (size_t)(r0 - 1) * W;
+                        m1u = row[2 * k + (qa ^ 1)]; m2u = row[2 * k + qa - W];
+                        if (nbu_ok) nbu = row[2 * keu + (qa ^ 1)];
+                    }
+                    if (has_dn) {
+                        const double *row = p.phi + (size_t)(r0 + NR) * W;
+                        m1d = row[2 * k + (qd ^ 1)]; m2d = row[2 * k + qd + W];
+                        if (nbd_ok) nbd = row[2 * ked + (qd ^ 1)];
+                    }
+                } else {
+                    if (has_up) {
+                        m1u = ll_consume(ru1, in_top + bin, seq, err, dead);
+                        m2u = ll_consume(ru2, in_top + bin + RES_NT, seq, err, dead);
+                        nbu = (qa == 0) ? __shfl_up_sync(amask, m1u, 1) : __shfl_down_sync(amask, m1u, 1);
+                        if (edge_u) nbu = ll_consume(rue, in_top + bin + (keu - k), seq, err, dead);
+                        if (!nbu_ok) nbu = 0.0;
+                    }
+                    if (has_dn) {
+                        m1d = ll_consume(rd1, in_bot + bin, seq, err, dead);
+                        m2d = ll_consume(rd2, in_bot + bin + RES_NT, seq, err, dead);
+                        nbd = (qd == 0) ? __shfl_up_sync(amask, m1d, 1) : __shfl_down_sync(amask, m1d, 1);
+                        if (edge_d) nbd = ll_consume(rde, in_bot + bin + (ked - k), seq, err, dead);
+                        if (!nbd_ok) nbd = 0.0;
+                    }
                 }
             }
             {
                 double halo_max = 0.0;   // the owner of a halo cell counts its update
                 const double nb0 = deep_nb<P0, 0, 0>(smk), nbl = deep_nb<P0, 0, NR - 1>(smk);
+                const double D0 = deep_D<NR, P0, 0, 0>(s, smD), Dl = deep_D<NR, P0, 0, NR - 1>(s, smD);
                 if (has_up)
                     s.hu = sor_cell(s.hu, (qa == 0) ? nbu : m1u, m2u, (qa == 0) ? m1u : nbu, s.v[0][qa], s.cM[qa], s.wM[qa], s.Du, halo_max);
                 if (has_dn)
                     s.hd = sor_cell(s.hd, (qd == 0) ? nbd : m1d, s.v[NR - 1][qd], (qd == 0) ? m1d : nbd, m2d, s.cM[qd], s.wM[qd], s.Dd, halo_max);
-                deep_cell<NR, P0, EDGE, 0, 0>(s, nb0, m1u, m1d, lmax);
-                deep_cell<NR, P0, EDGE, 0, NR - 1>(s, nbl, m1u, m1d, lmax);
+                deep_cell<NR, P0, EDGE, 0, 0>(s, nb0, D0, m1u, m1d, lmax);
+                deep_cell<NR, P0, EDGE, 0, NR - 1>(s, nbl, Dl, m1u, m1d, lmax);
                 smk[(0 * 2 + (P0 & 1)) * Kp] = s.v[0][P0 & 1];
                 smk[((NR - 1) * 2 + ((P0 + NR - 1) & 1)) * Kp] = s.v[NR - 1][(P0 + NR - 1) & 1];
             }
@@ -680,11 +790,11 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
         if (!idle) {
             // ---- colour 1: the rows the neighbours wait for first ------------------------------------
             const int bout = (sweep & 1) * 2 * RES_NT + k;
-            const unsigned seq_out = (unsigned)sweep + 1u;
+            const unsigned seq_out = (unsigned)sweep + 1u + SEQ0;
             constexpr int TOP = NR < 2 ? NR : 2;                    // rows [0, TOP) and [BOT, NR) are sent
             constexpr int BOT = (NR - 2 > TOP) ? NR - 2 : TOP;
-            deep_rows<NR, P0, EDGE, 1, 0, TOP>(s, smk, s.hu, s.hd, lmax);
-            deep_rows<NR, P0, EDGE, 1, BOT, NR>(s, smk, s.hu, s.hd, lmax);
+            deep_rows<NR, P0, EDGE, 1, 0, TOP>(s, smk, smD, s.hu, s.hd, lmax);
+            deep_rows<NR, P0, EDGE, 1, BOT, NR>(s, smk, smD, s.hu, s.hd, lmax);
             if (ll_up) {
                 ll_store(ll_up + bout, s.v[0][(P0 + 1) & 1], seq_out);
                 ll_store(ll_up + bout + RES_NT, s.v[1][P0 & 1], seq_out);
@@ -693,7 +803,7 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
                 ll_store(ll_dn + bout, s.v[NR - 1][(P0 + NR) & 1], seq_out);
                 ll_store(ll_dn + bout + RES_NT, s.v[NR - 2][(P0 + NR - 1) & 1], seq_out);
             }
-            deep_rows<NR, P0, EDGE, 1, TOP, BOT>(s, smk, s.hu, s.hd, lmax);
+            deep_rows<NR, P0, EDGE, 1, TOP, BOT>(s, smk, smD, s.hu, s.hd, lmax);
         }
         if (tid == 0) {   // convergence duty: the verdict on sweep e = sweep - lag (as in res_body)
             if (e >= 0 && conv_at == 0 && !errv) {
@@ -795,7 +905,8 @@ int resident_plan(pcd_solver *s) {
     const int Kp = RES_KP;
     s->res_ctas = P;
     s->res_rows_per_cta = pick;
-    s->res_smem = (size_t)pick * 2 * Kp * sizeof(double) + (size_t)2 * RES2_SLOTS * sizeof(uint4);  // + slots of the links inside a cluster
+    // phi (and, in the deep-halo kernel, D) of the slab + the slots of the links inside a cluster
+    s->res_smem = (size_t)pick * 2 * Kp * sizeof(double) * (DEEP_DSMEM ? 2 : 1) + (size_t)2 * RES2_SLOTS * sizeof(uint4);
     s->res_threads = RES_NT;
     return 1;
 }
@@ -853,8 +964,13 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
     unsigned long long *g_max = s->sweep_max;
     unsigned long long *g_slot = s->sweep_max + s->ring;
     // one exchange per sweep (deep halos) wherever its preconditions hold; a NaN in D is only found by the kernel itself
+    // Measured (tools/res_time.py, us per sweep deep / per-phase): slabs of 7 rows 1.65 / 2.35, 6 rows 1.72 / 2.12, 5 rows
+    // 1.64 / 1.97, 4 rows 1.86 / 1.71 (1024 x 512), 1.69 / 1.61 (512^2), 3 rows 1.64 / 1.58 (400^2): with fewer than five
+    // rows there is too little interior work to cover the one long exchange, and two short ones win.
     const bool no_deep = getenv("PCD_RES_NO_DEEP") != nullptr;   // read per solve: the tests compare both kernels
-    bool deep = !no_deep && W % 2 == 0 && s->res_rows_per_cta >= 3;
+    const char *min_rows_env = getenv("PCD_RES_DEEP_MIN_ROWS");  // tests: 3 = wherever the kernel is valid
+    const int min_rows = min_rows_env ? (atoi(min_rows_env) < 3 ? 3 : atoi(min_rows_env)) : 3;
+    bool deep = !no_deep && W % 2 == 0 && s->res_rows_per_cta >= min_rows;
     while (done < max_it && !conv) {
         const int k = max_it - done < RES_MAX_SWEEPS_PER_LAUNCH ? max_it - done : RES_MAX_SWEEPS_PER_LAUNCH;
         PCD_CUDA(cudaMemsetAsync(g_max, 0, sizeof(unsigned long long) * (size_t)k, s->stream));

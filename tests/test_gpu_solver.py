@@ -275,6 +275,7 @@ def test_resident_deep_halo_kernel_bit_exact(pcd, port, shape, monkeypatch):
     pinned to the oracle after 1, 2, 3, 10 and 41 sweeps, to the exchange-per-phase kernel after a converged run, on
     shapes with slabs of 2..7 rows, one to 512 column pairs, partly filled warps and single-lane warps."""
     H, W = shape
+    monkeypatch.setenv("PCD_RES_DEEP_MIN_ROWS", "3")   # by default slabs under five rows take the exchange-per-phase kernel
     rng = np.random.RandomState(7 * H + W)
     D = rng.standard_normal((H, W))
     D -= D.mean()
@@ -311,11 +312,11 @@ def test_resident_deep_halo_kernel_bit_exact(pcd, port, shape, monkeypatch):
 def test_resident_deep_halo_kernel_hands_nan_holes_back(pcd, port):
     """NaN holes need the masked neighbour rule: the deep-halo kernel finds them while loading, voids its launch without
     touching the field, and the exchange-per-phase kernel runs instead."""
-    H, W = 400, 400
+    H, W = 800, 400   # six rows per CTA: the deep-halo kernel is the default choice
     rng = np.random.RandomState(5)
     D = rng.standard_normal((H, W))
     D[100:140, 200:260] = np.nan
-    D[399, 399] = np.nan
+    D[799, 399] = np.nan
     phi0 = rng.standard_normal((H, W))
     s = pcd.Solver(W, H, 0, pcd.SOLVER_RESIDENT)
     s.upload(D, phi0)
@@ -329,3 +330,12 @@ def test_resident_deep_halo_kernel_hands_nan_holes_back(pcd, port):
     assert s.resident_exchange == 2 and info["launches"] == 1
     assert np.array_equal(s.download(), port.poisson_rb(D, phi0, 25, 0.0)[0])
     s.close()
+    # the default choice: the deep-halo kernel wherever it is valid (even width, at least three rows per CTA)
+    for (H2, W2, want_kernel) in ((400, 400, 2), (296, 64, 1), (400, 301, 1)):
+        s = pcd.Solver(W2, H2, 0, pcd.SOLVER_RESIDENT)
+        D = rng.standard_normal((H2, W2))
+        s.upload(D, np.zeros_like(D))
+        s.run(5, 0.0)
+        assert s.resident_exchange == want_kernel, (H2, W2)
+        assert np.array_equal(s.download(), port.poisson_rb(D, np.zeros_like(D), 5, 0.0)[0])
+        s.close()
