@@ -6,6 +6,8 @@
   mean-removed phi abs <= 1e-4
 * NaN holes, non-square grids (omega follows W), warm start, max_iterations cap, determinism
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -339,3 +341,37 @@ def test_resident_deep_halo_kernel_hands_nan_holes_back(pcd, port):
         assert s.resident_exchange == want_kernel, (H2, W2)
         assert np.array_equal(s.download(), port.poisson_rb(D, np.zeros_like(D), 5, 0.0)[0])
         s.close()
+
+
+_LAUNCH_MODE_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import poisson_caustic_design_b200 as P
+from oracle import oracle as O
+port = O.OracleLib()
+for (H, W) in ((600, 202), (1024, 1024)):
+    rng = np.random.RandomState(H + W)
+    D = rng.standard_normal((H, W)); D -= D.mean()
+    phi0 = rng.standard_normal((H, W))
+    s = P.Solver(W, H, 0, P.SOLVER_RESIDENT)
+    s.upload(D, phi0)
+    info = s.run(23, 0.0)
+    assert s.resident_exchange == int(sys.argv[2]), s.resident_exchange
+    assert np.array_equal(s.download(), port.poisson_rb(D, phi0, 23, 0.0)[0]), (H, W)
+    s.close()
+print("ok")
+"""
+
+
+@pytest.mark.parametrize("env,kernel", [({"PCD_RES_NO_PAIRS": "1"}, 2), ({"PCD_RES_NO_PAIRS": "1", "PCD_RES_NO_DEEP": "1"}, 1),
+                                        ({"PCD_RES_CLUSTER": "4"}, 2)])
+def test_resident_kernels_other_launch_modes(pcd, env, kernel):
+    """The cooperative launch without CTA pairs (every link through L2) and clusters of four are read from the environment
+    once per process, so they run in a child process: both resident kernels against the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _LAUNCH_MODE_SCRIPT, root, str(kernel)], env={**os.environ, **env},
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr

@@ -4,6 +4,7 @@
     compute-sanitizer --tool racecheck python tools/sanitize_run.py resident
 
 Cases: `resident` / `tiled` / `streaming` (K-SOR on 96x96 and 300x157, a few sweeps, checked against the oracle),
+`deep` (the resident kernel with one exchange per sweep: 64x444 and 40x740, three and five rows per CTA),
 `peer` (three slabs on one GPU driving the fused ghost-row exchange), `design` (init + one transport iteration + one
 height iteration on a 24x24 mesh).  Every case checks its result, so a sanitizer run that perturbs timing still has
 to produce the right bits."""
@@ -32,6 +33,19 @@ if case in ("resident", "tiled", "streaming"):
         s.upload(D, phi0)
         info = s.run(sweeps, 0.0)
         got = s.download()
+        s.close()
+        assert np.array_equal(got, port.poisson_rb(D, phi0, sweeps, 0.0)[0]), (case, h, w)
+        print(case, (h, w), "ok", info["path"], info["sweeps"], flush=True)
+elif case == "deep":
+    for (h, w) in ((444, 64), (740, 40)):
+        D = rng.standard_normal((h, w))
+        D -= D.mean()
+        phi0 = rng.standard_normal((h, w))
+        s = P.Solver(w, h, 0, P.SOLVER_RESIDENT)
+        s.upload(D, phi0)
+        info = s.run(sweeps, 0.0)
+        got = s.download()
+        assert s.resident_exchange == 2, "the deep-halo kernel did not run"
         s.close()
         assert np.array_equal(got, port.poisson_rb(D, phi0, sweeps, 0.0)[0]), (case, h, w)
         print(case, (h, w), "ok", info["path"], info["sweeps"], flush=True)
