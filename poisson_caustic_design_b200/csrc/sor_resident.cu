@@ -896,6 +896,10 @@ int resident_plan(pcd_solver *s) {
     if (K > RES_NT) return 0;
     int nr = (H + s->sm_count - 1) / s->sm_count;
     if (nr > RES_NR_MAX) return 0;
+    // short grids: fewer CTAs with three rows each rather than one or two rows on every SM, so that the kernel with one
+    // exchange per sweep applies (it needs even W and slabs of 3 / 2 rows; measured: three rows per CTA 1.18 us/sweep at
+    // 400^2 against 1.49 for two rows per CTA with an exchange per colour phase at 300 x 157)
+    if (nr < 3 && W % 2 == 0 && H >= 3) nr = 3;
     // rows are split as evenly as possible: P slabs, the first n_big of nr rows and the rest of nr-1, so no slab has
     // phantom rows (a partly filled slab would run the per-cell masked path and set the pace of the whole chain:
     // 1000 x 1000 took 4.98 us/sweep with one 6-of-7 slab against 3.0 us for 1024 x 1024)

@@ -332,8 +332,9 @@ def test_resident_deep_halo_kernel_hands_nan_holes_back(pcd, port):
     assert s.resident_exchange == 2 and info["launches"] == 1
     assert np.array_equal(s.download(), port.poisson_rb(D, phi0, 25, 0.0)[0])
     s.close()
-    # the default choice: the deep-halo kernel wherever it is valid (even width, at least three rows per CTA)
-    for (H2, W2, want_kernel) in ((400, 400, 2), (296, 64, 1), (400, 301, 1)):
+    # the default choice: the deep-halo kernel wherever it is valid (even width, at least three rows; short grids get
+    # fewer CTAs of three rows each), the exchange-per-phase kernel for odd widths and grids of one or two rows
+    for (H2, W2, want_kernel) in ((400, 400, 2), (296, 64, 2), (157, 300, 2), (2, 64, 1), (400, 301, 1)):
         s = pcd.Solver(W2, H2, 0, pcd.SOLVER_RESIDENT)
         D = rng.standard_normal((H2, W2))
         s.upload(D, np.zeros_like(D))
