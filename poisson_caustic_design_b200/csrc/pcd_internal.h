@@ -91,6 +91,9 @@ struct pcd_solver {
 };
 
 namespace pcd {
+// run_resident's way of saying "not on chip after all" (never leaves solver_run): strips of 8-9 rows exist only in the
+// deep-halo kernel, which does not take NaN holes
+constexpr int PCD_RES_FALLBACK = 1000;
 int solver_init(pcd_solver *s, int W, int H, int device, int path, cudaStream_t stream);
 void solver_free(pcd_solver *s);
 // D_dev / phi_dev: device arrays of W*H doubles; phi in/out

@@ -346,10 +346,17 @@ int solver_run(pcd_solver *s, const double *D, double *phi, int max_iterations, 
     PCD_TRY(select_device(s->device));
     if (max_iterations <= 0) return PCD_OK;  // the reference's loop body never runs (src/solver.cpp:92)
     PCD_CUDA(cudaEventRecord(s->ev0, s->stream));
-    int rc;
-    if (s->path_used == PCD_SOLVER_RESIDENT) {
+    int rc = PCD_OK;
+    int path = s->path_used;
+    if (path == PCD_SOLVER_RESIDENT) {
         rc = run_resident(s, D, phi, max_iterations, tol, info);
-    } else {
+        if (rc == PCD_RES_FALLBACK) {   // strips of 8-9 rows only exist in the deep-halo kernel, and D has NaN holes: large-grid paths
+            *info = pcd_solve_info{};
+            path = PCD_SOLVER_TILED;
+            info->path = path;
+        }
+    }
+    if (path != PCD_SOLVER_RESIDENT) {
         // NaN holes change the neighbour rule (src/solver.cpp:29-44); only then is a mask array built
         const long n = (long)s->W * s->H;
         PCD_CUDA(cudaMemsetAsync(s->d_flags, 0, sizeof(int), s->stream));
@@ -367,9 +374,9 @@ int solver_run(pcd_solver *s, const double *D, double *phi, int max_iterations, 
         }
         // the tiled path derives neighbour counts from coordinates, the direct backend needs the plain operator: NaN
         // holes go through the masked colour kernels
-        if (s->path_used == PCD_SOLVER_TILED && !masked) {
+        if (path == PCD_SOLVER_TILED && !masked) {
             rc = run_tiled(s, D, phi, max_iterations, tol, info);
-        } else if (s->path_used == PCD_SOLVER_DCT && !masked) {
+        } else if (path == PCD_SOLVER_DCT && !masked) {
             rc = run_dct(s, D, phi, info);
         } else {
             info->path = PCD_SOLVER_STREAMING;

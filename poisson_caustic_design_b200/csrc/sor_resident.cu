@@ -37,6 +37,9 @@ namespace pcd {
 
 constexpr int RES_NT = 512;     // 16 warps = 4 per SM sub-partition -> 128 registers per thread
 constexpr int RES_NR_MAX = 7;   // rows per slab (2*NR phi + 2*NR D doubles per thread)
+// The deep-halo kernel keeps D in shared memory, so its strips can be taller: 9 rows = 36 phi registers per thread and
+// 209 KB of shared memory per CTA (grids up to 1024 x 1332; the exchange-per-phase kernel stops at RES_NR_MAX).
+constexpr int RES_NR_DEEP_MAX = 9;
 constexpr int RES_KP = RES_NT + 4;  // smem pitch of one parity row: compile-time so every smem offset is an immediate
 // Halo slots of one link and direction: [parity][RES_NT] x 16 B, the message of column x = 2k+q in slot q * RES_NT + k.
 // Dense per parity: the 32 messages a warp sends in a phase fill 16 whole 32-byte sectors (with one slot per COLUMN, as
@@ -895,7 +898,8 @@ int resident_plan(pcd_solver *s) {
     const int K = (W + 1) / 2;
     if (K > RES_NT) return 0;
     int nr = (H + s->sm_count - 1) / s->sm_count;
-    if (nr > RES_NR_MAX) return 0;
+    // 8 or 9 rows per CTA: only the deep-halo kernel (even W); NaN holes then go to the large-grid paths (run_resident)
+    if (nr > RES_NR_MAX && (nr > RES_NR_DEEP_MAX || W % 2 != 0)) return 0;
     // short grids: fewer CTAs with three rows each rather than one or two rows on every SM, so that the kernel with one
     // exchange per sweep applies (it needs even W and slabs of 3 / 2 rows; measured: three rows per CTA 1.18 us/sweep at
     // 400^2 against 1.49 for two rows per CTA with an exchange per colour phase at 300 x 157)
@@ -917,10 +921,12 @@ int resident_plan(pcd_solver *s) {
 
 template <int NR>
 static int launch_resident(pcd_solver *s, ResParams &prm, bool deep) {
-    void (*kernel)(const ResParams) = sor_resident_kernel<NR>;
+    void (*kernel)(const ResParams) = nullptr;
+    if constexpr (NR <= RES_NR_MAX) kernel = sor_resident_kernel<NR>;
     if constexpr (NR >= 3) {
         if (deep) kernel = sor_resident_deep_kernel<NR>;
     }
+    if (!kernel) { set_error("resident K-SOR: no kernel for %d rows per CTA without deep halos", NR); return PCD_ERR_UNSUPPORTED; }
     PCD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->res_smem));
     // preferred: clusters of two CTAs (one TPC each); the link inside a pair then runs over DSMEM and only every other
     // link crosses L2.  This launch carries the cluster attribute only (cluster + cooperative is refused under the
@@ -975,6 +981,8 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
     const char *min_rows_env = getenv("PCD_RES_DEEP_MIN_ROWS");  // tests: 3 = wherever the kernel is valid
     const int min_rows = min_rows_env ? (atoi(min_rows_env) < 3 ? 3 : atoi(min_rows_env)) : 3;
     bool deep = !no_deep && W % 2 == 0 && s->res_rows_per_cta >= min_rows;
+    const bool deep_only = s->res_rows_per_cta > RES_NR_MAX;   // strips too tall for the exchange-per-phase kernel
+    if (deep_only && !deep) return PCD_RES_FALLBACK;
     while (done < max_it && !conv) {
         const int k = max_it - done < RES_MAX_SWEEPS_PER_LAUNCH ? max_it - done : RES_MAX_SWEEPS_PER_LAUNCH;
         PCD_CUDA(cudaMemsetAsync(g_max, 0, sizeof(unsigned long long) * (size_t)k, s->stream));
@@ -995,7 +1003,9 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
             case 4: rc = launch_resident<4>(s, prm, deep); break;
             case 5: rc = launch_resident<5>(s, prm, deep); break;
             case 6: rc = launch_resident<6>(s, prm, deep); break;
-            default: rc = launch_resident<7>(s, prm, deep); break;
+            case 7: rc = launch_resident<7>(s, prm, deep); break;
+            case 8: rc = launch_resident<8>(s, prm, deep); break;
+            default: rc = launch_resident<9>(s, prm, deep); break;
         }
         PCD_TRY(rc);
         PCD_CUDA(cudaEventRecord(s->evk1, s->stream));
@@ -1003,7 +1013,11 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
         PCD_CUDA(cudaMemcpyAsync(s->h_res_state, s->res_state, sizeof(ResState), cudaMemcpyDeviceToHost, s->stream));
         PCD_CUDA(cudaStreamSynchronize(s->stream));
         const ResState st = *(ResState *)s->h_res_state;
-        if (st.error == RES_ERR_UNSUPPORTED && deep) { deep = false; continue; }   // NaN holes: phi is untouched
+        if (st.error == RES_ERR_UNSUPPORTED && deep) {   // NaN holes: phi is untouched
+            if (deep_only) return PCD_RES_FALLBACK;
+            deep = false;
+            continue;
+        }
         if (st.error) {  // a CTA waited in vain: phi is untouched
             if (s->res_pairs == 1) { s->res_pairs = -1; continue; }   // once more, cooperatively
             set_error("resident K-SOR kernel: a CTA gave up waiting for its neighbour");

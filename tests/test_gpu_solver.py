@@ -270,7 +270,7 @@ def test_check_lag_is_clamped(pcd, port):
 
 
 @pytest.mark.parametrize("shape", [(400, 400), (444, 64), (298, 36), (297, 66), (600, 202), (740, 6), (1036, 1024), (1024, 1024),
-                                   (512, 130), (900, 1000)])
+                                   (512, 130), (900, 1000), (1100, 600), (1332, 64), (1300, 1024), (157, 300), (96, 96), (5, 8)])
 def test_resident_deep_halo_kernel_bit_exact(pcd, port, shape, monkeypatch):
     """The resident kernel with ONE neighbour exchange per sweep (redundant update of the colour-0 cells of the rows just
     outside a slab, double-buffered messages, lane shuffles + edge-lane polls for the halo row's left/right cells):
@@ -304,10 +304,33 @@ def test_resident_deep_halo_kernel_bit_exact(pcd, port, shape, monkeypatch):
     monkeypatch.setenv("PCD_RES_NO_DEEP", "1")
     s.upload(D2, z)
     classic = s.run(100000, 1e-6)
-    assert s.resident_exchange == 1
-    assert classic["converged_at"] == deep["converged_at"] and classic["sweeps"] == deep["sweeps"]
-    assert np.array_equal(s.download(), f_deep)
-    assert classic["last_max_update"] == deep["last_max_update"]
+    # strips of 8-9 rows (H > 1036) exist only in the deep-halo kernel: without it the solve runs on the wavefront path
+    assert s.resident_exchange == (1 if H <= 1036 else 0)
+    assert classic["converged_at"] == deep["converged_at"]
+    if H <= 1036:
+        assert classic["sweeps"] == deep["sweeps"]
+        assert np.array_equal(s.download(), f_deep)
+        assert classic["last_max_update"] == deep["last_max_update"]
+    s.close()
+
+
+def test_resident_tall_strips_hand_nan_holes_to_the_large_grid_path(pcd, port):
+    """1100 rows = 8 rows per CTA: on chip only with the deep-halo kernel, which does not take NaN holes -- the solve then
+    runs on the masked large-grid path, same bits as the oracle."""
+    H, W = 1100, 256
+    rng = np.random.RandomState(11)
+    D = rng.standard_normal((H, W))
+    phi0 = rng.standard_normal((H, W))
+    s = pcd.Solver(W, H, 0, pcd.SOLVER_AUTO)
+    s.upload(D, phi0)
+    info = s.run(9, 0.0)
+    assert s.resident_exchange == 2 and info["path"] == "resident"
+    assert np.array_equal(s.download(), port.poisson_rb(D, phi0, 9, 0.0)[0])
+    D[500:520, 100:130] = np.nan
+    s.upload(D, phi0)
+    info = s.run(9, 0.0)
+    assert s.resident_exchange == 0 and info["path"] == "streaming" and info["sweeps"] == 9
+    assert np.array_equal(s.download(), port.poisson_rb(D, phi0, 9, 0.0)[0], equal_nan=True)
     s.close()
 
 
