@@ -83,6 +83,8 @@ struct pcd_solver {
     cudaEvent_t ev_blk[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     void *dct_state = nullptr;      // opt-in direct backend (dct_solver.cu): DCT matrices, eigenvalues, temporaries
     int res_ctas = 0, res_threads = 0, res_rows_per_cta = 0, res_n_big = 0;
+    bool res_tr = false;              // resident solve on the TRANSPOSED grid (W > 1024 columns but H <= 1024 rows)
+    double *tr_D = nullptr, *tr_phi = nullptr;   // its transposed copies of D and phi (H x W doubles each, allocated on first use)
     int res_exchange = 0;   // resident kernel of the last run: 0 none, 1 exchange per colour phase, 2 per sweep (deep halos)
     int res_pairs = 0;   // CTA-pair (cluster) launch of the resident kernel: 0 undecided, 1 in use, -1 not available
     size_t res_smem = 0;

@@ -323,6 +323,7 @@ void solver_free(pcd_solver *s) {
     cudaFree(s->mask); cudaFree(s->d_flags); cudaFreeHost(s->h_flags);
     cudaFree(s->res_state); cudaFreeHost(s->h_res_state); cudaFree(s->halo); cudaFree(s->phi_alt); cudaFree(s->wave_ctl);
     cudaFree(s->d_split);
+    cudaFree(s->tr_D); cudaFree(s->tr_phi);
     if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
     for (int i = 0; i < 2; ++i) {
         if (s->ev_blk[i]) cudaEventDestroy(s->ev_blk[i]);

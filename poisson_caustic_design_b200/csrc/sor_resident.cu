@@ -500,6 +500,14 @@ __device__ __forceinline__ double sor_cell(const double val, const double l, con
     return val + delta;
 }
 
+// Transposed solves (TR): the kernel's left/up/right/down are the grid's up/left/down/right, so the reference's summation
+// order ((l + u) + r) + d reads ((l' + u') + d') + r' here (l + u commutes bit for bit; the last two additions swap)
+template <bool TR>
+__device__ __forceinline__ double sor_cell_o(const double val, const double l, const double u, const double r, const double d,
+                                             const double cnt, const double wv, const double Dv, double &lmax) {
+    return TR ? sor_cell(val, l, u, d, r, cnt, wv, Dv, lmax) : sor_cell(val, l, u, r, d, cnt, wv, Dv, lmax);
+}
+
 template <int NR>
 struct DeepStrip {
     double v[NR][2], D[DEEP_DSMEM ? 1 : NR][2];   // D: registers, or shared memory (DEEP_DSMEM)
@@ -508,7 +516,7 @@ struct DeepStrip {
 };
 
 // update of the colour-C cell of slab row J (P0 = column parity of the colour-0 cell of row 0)
-template <int NR, int P0, bool EDGE, int C, int J>
+template <int NR, int P0, bool EDGE, bool TR, int C, int J>
 __device__ __forceinline__ void deep_cell(DeepStrip<NR> &s, const double nb, const double Dv, const double upv, const double dnv, double &lmax) {
     constexpr int q = (P0 + C + J) & 1;
     const double own = s.v[J][q ^ 1];
@@ -517,7 +525,7 @@ __device__ __forceinline__ void deep_cell(DeepStrip<NR> &s, const double nb, con
     const double d = (J == NR - 1) ? dnv : s.v[(J == NR - 1) ? J : J + 1][q];
     const double cnt = (EDGE && J == 0) ? s.cT[q] : ((EDGE && J == NR - 1) ? s.cB[q] : s.cM[q]);
     const double wv = (EDGE && J == 0) ? s.wT[q] : ((EDGE && J == NR - 1) ? s.wB[q] : s.wM[q]);
-    s.v[J][q] = sor_cell(s.v[J][q], l, u, r, d, cnt, wv, Dv, lmax);
+    s.v[J][q] = sor_cell_o<TR>(s.v[J][q], l, u, r, d, cnt, wv, Dv, lmax);
 }
 
 // D of the colour-C cell of row J: a register, or this thread's own shared-memory word (unit stride over the warp)
@@ -535,7 +543,7 @@ __device__ __forceinline__ double deep_nb(const double *__restrict__ smk) {
 }
 
 // rows [A, B) of colour C: all shared-memory reads, then the arithmetic, then the writes
-template <int NR, int P0, bool EDGE, int C, int A, int B>
+template <int NR, int P0, bool EDGE, bool TR, int C, int A, int B>
 __device__ __forceinline__ void deep_rows(DeepStrip<NR> &s, double *__restrict__ smk, const double *__restrict__ smD,
                                           const double upv, const double dnv, double &lmax) {
     if constexpr (A < B) {
@@ -547,7 +555,7 @@ __device__ __forceinline__ void deep_rows(DeepStrip<NR> &s, double *__restrict__
         });
         static_rows<A, B>([&](auto Jc) {
             constexpr int J = decltype(Jc)::value;
-            deep_cell<NR, P0, EDGE, C, J>(s, nb[J - A], dv[J - A], upv, dnv, lmax);
+            deep_cell<NR, P0, EDGE, TR, C, J>(s, nb[J - A], dv[J - A], upv, dnv, lmax);
         });
         static_rows<A, B>([&](auto Jc) {
             constexpr int J = decltype(Jc)::value, q = (P0 + C + J) & 1;
@@ -556,7 +564,7 @@ __device__ __forceinline__ void deep_rows(DeepStrip<NR> &s, double *__restrict__
     }
 }
 
-template <int NR, int P0, bool EDGE>
+template <int NR, int P0, bool EDGE, bool TR>
 __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
     static_assert(NR >= 2, "deep halos need two rows per slab");
     extern __shared__ double smem[];  // phi [nr_big][2][Kp] as in res_body, D likewise (DEEP_DSMEM), then the slots of the links inside a cluster
@@ -689,12 +697,12 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
                 // the first poll is issued after SPLIT - 1 of the interior rows: late enough to find the message, early
                 // enough for the rest of the interior to cover its latency
                 constexpr int SPLIT = (1 + PCD_DEEP_POLL_AFTER < NR - 1) ? 1 + PCD_DEEP_POLL_AFTER : (NR - 1 > 1 ? NR - 1 : 1);
-                deep_rows<NR, P0, EDGE, 0, 1, SPLIT>(s, smk, smD, 0.0, 0.0, lmax);
+                deep_rows<NR, P0, EDGE, TR, 0, 1, SPLIT>(s, smk, smD, 0.0, 0.0, lmax);
                 if (!first) {
                     if (has_up) { ru1 = ll_issue(in_top + bin); ru2 = ll_issue(in_top + bin + RES_NT); if (edge_u) rue = ll_issue(in_top + bin + (keu - k)); }
                     if (has_dn) { rd1 = ll_issue(in_bot + bin); rd2 = ll_issue(in_bot + bin + RES_NT); if (edge_d) rde = ll_issue(in_bot + bin + (ked - k)); }
                 }
-                deep_rows<NR, P0, EDGE, 0, SPLIT, NR - 1>(s, smk, smD, 0.0, 0.0, lmax);
+                deep_rows<NR, P0, EDGE, TR, 0, SPLIT, NR - 1>(s, smk, smD, 0.0, 0.0, lmax);
                 if (first) {   // (!DEEP_PRESEND) the halo rows of the first sweep come from the input field
                     if (has_up) {
                         const double *row = p.phi + (size_t)(r0 - 1) * W;
@@ -742,7 +750,7 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
                     if (has_up) { ru1 = ll_issue(in_top + bin); ru2 = ll_issue(in_top + bin + RES_NT); if (edge_u) rue = ll_issue(in_top + bin + (keu - k)); }
                     if (has_dn) { rd1 = ll_issue(in_bot + bin); rd2 = ll_issue(in_bot + bin + RES_NT); if (edge_d) rde = ll_issue(in_bot + bin + (ked - k)); }
                 }
-                deep_rows<NR, P0, EDGE, 0, 1, NR - 1>(s, smk, smD, 0.0, 0.0, lmax);
+                deep_rows<NR, P0, EDGE, TR, 0, 1, NR - 1>(s, smk, smD, 0.0, 0.0, lmax);
                 if (first) {   // the halo rows of the first sweep come from the input field (untouched until every CTA is done)
                     if (has_up) {
                         const double *row = p.phi + (size_t)(r0 - 1) * W;
@@ -776,11 +784,11 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
                 const double nb0 = deep_nb<P0, 0, 0>(smk), nbl = deep_nb<P0, 0, NR - 1>(smk);
                 const double D0 = deep_D<NR, P0, 0, 0>(s, smD), Dl = deep_D<NR, P0, 0, NR - 1>(s, smD);
                 if (has_up)
-                    s.hu = sor_cell(s.hu, (qa == 0) ? nbu : m1u, m2u, (qa == 0) ? m1u : nbu, s.v[0][qa], s.cM[qa], s.wM[qa], s.Du, halo_max);
+                    s.hu = sor_cell_o<TR>(s.hu, (qa == 0) ? nbu : m1u, m2u, (qa == 0) ? m1u : nbu, s.v[0][qa], s.cM[qa], s.wM[qa], s.Du, halo_max);
                 if (has_dn)
-                    s.hd = sor_cell(s.hd, (qd == 0) ? nbd : m1d, s.v[NR - 1][qd], (qd == 0) ? m1d : nbd, m2d, s.cM[qd], s.wM[qd], s.Dd, halo_max);
-                deep_cell<NR, P0, EDGE, 0, 0>(s, nb0, D0, m1u, m1d, lmax);
-                deep_cell<NR, P0, EDGE, 0, NR - 1>(s, nbl, Dl, m1u, m1d, lmax);
+                    s.hd = sor_cell_o<TR>(s.hd, (qd == 0) ? nbd : m1d, s.v[NR - 1][qd], (qd == 0) ? m1d : nbd, m2d, s.cM[qd], s.wM[qd], s.Dd, halo_max);
+                deep_cell<NR, P0, EDGE, TR, 0, 0>(s, nb0, D0, m1u, m1d, lmax);
+                deep_cell<NR, P0, EDGE, TR, 0, NR - 1>(s, nbl, Dl, m1u, m1d, lmax);
                 smk[(0 * 2 + (P0 & 1)) * Kp] = s.v[0][P0 & 1];
                 smk[((NR - 1) * 2 + ((P0 + NR - 1) & 1)) * Kp] = s.v[NR - 1][(P0 + NR - 1) & 1];
             }
@@ -796,8 +804,8 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
             const unsigned seq_out = (unsigned)sweep + 1u + SEQ0;
             constexpr int TOP = NR < 2 ? NR : 2;                    // rows [0, TOP) and [BOT, NR) are sent
             constexpr int BOT = (NR - 2 > TOP) ? NR - 2 : TOP;
-            deep_rows<NR, P0, EDGE, 1, 0, TOP>(s, smk, smD, s.hu, s.hd, lmax);
-            deep_rows<NR, P0, EDGE, 1, BOT, NR>(s, smk, smD, s.hu, s.hd, lmax);
+            deep_rows<NR, P0, EDGE, TR, 1, 0, TOP>(s, smk, smD, s.hu, s.hd, lmax);
+            deep_rows<NR, P0, EDGE, TR, 1, BOT, NR>(s, smk, smD, s.hu, s.hd, lmax);
             if (ll_up) {
                 ll_store(ll_up + bout, s.v[0][(P0 + 1) & 1], seq_out);
                 ll_store(ll_up + bout + RES_NT, s.v[1][P0 & 1], seq_out);
@@ -806,7 +814,7 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
                 ll_store(ll_dn + bout, s.v[NR - 1][(P0 + NR) & 1], seq_out);
                 ll_store(ll_dn + bout + RES_NT, s.v[NR - 2][(P0 + NR - 1) & 1], seq_out);
             }
-            deep_rows<NR, P0, EDGE, 1, TOP, BOT>(s, smk, smD, s.hu, s.hd, lmax);
+            deep_rows<NR, P0, EDGE, TR, 1, TOP, BOT>(s, smk, smD, s.hu, s.hd, lmax);
         }
         if (tid == 0) {   // convergence duty: the verdict on sweep e = sweep - lag (as in res_body)
             if (e >= 0 && conv_at == 0 && !errv) {
@@ -868,7 +876,7 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
     }
 }
 
-template <int NR>
+template <int NR, bool TR>
 __global__ void __launch_bounds__(RES_NT, 1) sor_resident_deep_kernel(const __grid_constant__ ResParams p) {
     const int c = (int)blockIdx.x;
     const bool edge = c == 0 || c + 1 == p.P;
@@ -880,11 +888,11 @@ __global__ void __launch_bounds__(RES_NT, 1) sor_resident_deep_kernel(const __gr
     const bool big = c < p.n_big;
     const int r0 = big ? c * NR : p.n_big * NR + (c - p.n_big) * (NR - 1);
     if (big) {
-        if (edge) { if (r0 & 1) deep_body<NR, 1, true>(p, r0); else deep_body<NR, 0, true>(p, r0); }
-        else      { if (r0 & 1) deep_body<NR, 1, false>(p, r0); else deep_body<NR, 0, false>(p, r0); }
+        if (edge) { if (r0 & 1) deep_body<NR, 1, true, TR>(p, r0); else deep_body<NR, 0, true, TR>(p, r0); }
+        else      { if (r0 & 1) deep_body<NR, 1, false, TR>(p, r0); else deep_body<NR, 0, false, TR>(p, r0); }
     } else {
-        if (edge) { if (r0 & 1) deep_body<NR - 1, 1, true>(p, r0); else deep_body<NR - 1, 0, true>(p, r0); }
-        else      { if (r0 & 1) deep_body<NR - 1, 1, false>(p, r0); else deep_body<NR - 1, 0, false>(p, r0); }
+        if (edge) { if (r0 & 1) deep_body<NR - 1, 1, true, TR>(p, r0); else deep_body<NR - 1, 0, true, TR>(p, r0); }
+        else      { if (r0 & 1) deep_body<NR - 1, 1, false, TR>(p, r0); else deep_body<NR - 1, 0, false, TR>(p, r0); }
     }
 }
 
@@ -893,17 +901,31 @@ __global__ void __launch_bounds__(RES_NT, 1) sor_resident_deep_kernel(const __gr
 // ------------------------------------------------------------------------------------------------
 int resident_slots() { return RES2_SLOTS; }
 
-int resident_plan(pcd_solver *s) {
-    const int W = s->W, H = s->H;
-    const int K = (W + 1) / 2;
-    if (K > RES_NT) return 0;
-    int nr = (H + s->sm_count - 1) / s->sm_count;
+// rows per CTA for a Wk x Hk kernel grid (0: does not fit on chip)
+static int resident_rows(const pcd_solver *s, int Wk, int Hk, bool deep_only) {
+    if ((Wk + 1) / 2 > RES_NT) return 0;
+    int nr = (Hk + s->sm_count - 1) / s->sm_count;
     // 8 or 9 rows per CTA: only the deep-halo kernel (even W); NaN holes then go to the large-grid paths (run_resident)
-    if (nr > RES_NR_MAX && (nr > RES_NR_DEEP_MAX || W % 2 != 0)) return 0;
+    if (nr > RES_NR_DEEP_MAX || ((nr > RES_NR_MAX || deep_only) && Wk % 2 != 0)) return 0;
     // short grids: fewer CTAs with three rows each rather than one or two rows on every SM, so that the kernel with one
     // exchange per sweep applies (it needs even W and slabs of 3 / 2 rows; measured: three rows per CTA 1.18 us/sweep at
     // 400^2 against 1.49 for two rows per CTA with an exchange per colour phase at 300 x 157)
-    if (nr < 3 && W % 2 == 0 && H >= 3) nr = 3;
+    if (nr < 3 && Wk % 2 == 0 && Hk >= 3) nr = 3;
+    if (deep_only && nr < 3) return 0;
+    return nr;
+}
+
+int resident_plan(pcd_solver *s) {
+    // Wide grids (more than 1024 columns) whose HEIGHT fits the thread layout are solved transposed, by the deep-halo
+    // kernel only (its summation order is a template switch, sor_cell_o): 1280 x 720 runs as 720 x 1280.
+    s->res_tr = false;
+    int nr = resident_rows(s, s->W, s->H, false);
+    if (!nr) {
+        nr = resident_rows(s, s->H, s->W, true);
+        if (!nr) return 0;
+        s->res_tr = true;
+    }
+    const int H = s->res_tr ? s->W : s->H;   // rows of the kernel's grid
     // rows are split as evenly as possible: P slabs, the first n_big of nr rows and the rest of nr-1, so no slab has
     // phantom rows (a partly filled slab would run the per-cell masked path and set the pace of the whole chain:
     // 1000 x 1000 took 4.98 us/sweep with one 6-of-7 slab against 3.0 us for 1024 x 1024)
@@ -919,12 +941,33 @@ int resident_plan(pcd_solver *s) {
     return 1;
 }
 
+// out[x][y] = in[y][x] for a W x H row-major field (32 x 32 tiles through shared memory, both sides coalesced)
+__global__ void transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int W, int H) {
+    __shared__ double tile[32][33];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int x = x0 + threadIdx.x, y = y0 + j;
+        if (x < W && y < H) tile[j][threadIdx.x] = in[(size_t)y * W + x];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int y = y0 + threadIdx.x, x = x0 + j;
+        if (x < W && y < H) out[(size_t)x * H + y] = tile[threadIdx.x][j];
+    }
+}
+
+static int transpose_field(const double *in, double *out, int W, int H, cudaStream_t stream) {
+    transpose_kernel<<<dim3((W + 31) / 32, (H + 31) / 32), dim3(32, 8), 0, stream>>>(in, out, W, H);
+    PCD_LAUNCHED();
+    return PCD_OK;
+}
+
 template <int NR>
 static int launch_resident(pcd_solver *s, ResParams &prm, bool deep) {
     void (*kernel)(const ResParams) = nullptr;
     if constexpr (NR <= RES_NR_MAX) kernel = sor_resident_kernel<NR>;
     if constexpr (NR >= 3) {
-        if (deep) kernel = sor_resident_deep_kernel<NR>;
+        if (deep) kernel = s->res_tr ? sor_resident_deep_kernel<NR, true> : sor_resident_deep_kernel<NR, false>;
     }
     if (!kernel) { set_error("resident K-SOR: no kernel for %d rows per CTA without deep halos", NR); return PCD_ERR_UNSUPPORTED; }
     PCD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->res_smem));
@@ -966,7 +1009,8 @@ static int launch_resident(pcd_solver *s, ResParams &prm, bool deep) {
 }
 
 int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double tol, pcd_solve_info *info) {
-    const int W = s->W, H = s->H;
+    const bool tr = s->res_tr;
+    const int W = tr ? s->H : s->W, H = tr ? s->W : s->H;   // the kernel's grid (the transposed one for wide grids)
     const int P = s->res_ctas;
     const int lag = s->check_lag > 0 ? s->check_lag : 4;  // >= 1: a sweep's slot is complete only after every CTA left it
     int done = 0, conv = 0;
@@ -981,8 +1025,18 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
     const char *min_rows_env = getenv("PCD_RES_DEEP_MIN_ROWS");  // tests: 3 = wherever the kernel is valid
     const int min_rows = min_rows_env ? (atoi(min_rows_env) < 3 ? 3 : atoi(min_rows_env)) : 3;
     bool deep = !no_deep && W % 2 == 0 && s->res_rows_per_cta >= min_rows;
-    const bool deep_only = s->res_rows_per_cta > RES_NR_MAX;   // strips too tall for the exchange-per-phase kernel
+    const bool deep_only = s->res_rows_per_cta > RES_NR_MAX || tr;   // strips too tall for the exchange-per-phase kernel, or transposed
     if (deep_only && !deep) return PCD_RES_FALLBACK;
+    if (tr) {   // the kernel works on transposed copies; phi itself is only written after a completed solve
+        const size_t bytes = sizeof(double) * (size_t)W * H;
+        if (!s->tr_D) PCD_CUDA(cudaMalloc(&s->tr_D, bytes));
+        if (!s->tr_phi) PCD_CUDA(cudaMalloc(&s->tr_phi, bytes));
+        PCD_TRY(transpose_field(D, s->tr_D, s->W, s->H, s->stream));
+        PCD_TRY(transpose_field(phi, s->tr_phi, s->W, s->H, s->stream));
+        info->launches += 2;
+    }
+    const double *Dk = tr ? s->tr_D : D;
+    double *phik = tr ? s->tr_phi : phi;
     while (done < max_it && !conv) {
         const int k = max_it - done < RES_MAX_SWEEPS_PER_LAUNCH ? max_it - done : RES_MAX_SWEEPS_PER_LAUNCH;
         PCD_CUDA(cudaMemsetAsync(g_max, 0, sizeof(unsigned long long) * (size_t)k, s->stream));
@@ -990,9 +1044,9 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
         PCD_CUDA(cudaMemsetAsync(s->halo, 0, (size_t)P * 2 * RES2_SLOTS * sizeof(uint4), s->stream));
         PCD_CUDA(cudaMemsetAsync(s->res_state, 0, sizeof(ResState), s->stream));
         ResParams prm;
-        prm.phi = phi; prm.D = D; prm.W = W; prm.H = H; prm.K = (W + 1) / 2;
+        prm.phi = phik; prm.D = Dk; prm.W = W; prm.H = H; prm.K = (W + 1) / 2;
         prm.Kp = RES_KP;
-        prm.P = P; prm.n_big = s->res_n_big; prm.nr_big = s->res_rows_per_cta; prm.max_it = k; prm.lag = lag; prm.tol = tol; prm.w = make_w(W);
+        prm.P = P; prm.n_big = s->res_n_big; prm.nr_big = s->res_rows_per_cta; prm.max_it = k; prm.lag = lag; prm.tol = tol; prm.w = make_w(s->W);   // omega follows the GRID's width (src/solver.cpp:71), transposed or not
         prm.ll = (uint4 *)s->halo; prm.g_max = g_max; prm.g_slot = g_slot; prm.state = (ResState *)s->res_state;
         int rc;
         PCD_CUDA(cudaEventRecord(s->evk0, s->stream));
@@ -1042,6 +1096,10 @@ int run_resident(pcd_solver *s, const double *D, double *phi, int max_it, double
         if (conv_local) conv = done + conv_local;
         done += st.sweeps;
         s->res_exchange = deep ? 2 : 1;
+    }
+    if (tr) {
+        PCD_TRY(transpose_field(s->tr_phi, phi, W, H, s->stream));
+        info->launches++;
     }
     info->sweeps = done;
     info->converged_at = conv;

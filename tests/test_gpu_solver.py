@@ -270,14 +270,15 @@ def test_check_lag_is_clamped(pcd, port):
 
 
 @pytest.mark.parametrize("shape", [(400, 400), (444, 64), (298, 36), (297, 66), (600, 202), (740, 6), (1036, 1024), (1024, 1024),
-                                   (512, 130), (900, 1000), (1100, 600), (1332, 64), (1300, 1024), (157, 300), (96, 96), (5, 8)])
+                                   (512, 130), (900, 1000), (1100, 600), (1332, 64), (1300, 1024), (157, 300), (96, 96), (5, 8),
+                                   (720, 1280), (400, 1100), (1024, 1332), (64, 1200), (4, 1030)])
 def test_resident_deep_halo_kernel_bit_exact(pcd, port, shape, monkeypatch):
     """The resident kernel with ONE neighbour exchange per sweep (redundant update of the colour-0 cells of the rows just
     outside a slab, double-buffered messages, lane shuffles + edge-lane polls for the halo row's left/right cells):
     pinned to the oracle after 1, 2, 3, 10 and 41 sweeps, to the exchange-per-phase kernel after a converged run, on
-    shapes with slabs of 2..7 rows, one to 512 column pairs, partly filled warps and single-lane warps."""
+    shapes with slabs of 2..9 rows, one to 512 column pairs, partly filled warps and single-lane warps, and on grids
+    wider than 1024 columns, which are solved transposed (summation order switched so the bits stay the reference's)."""
     H, W = shape
-    monkeypatch.setenv("PCD_RES_DEEP_MIN_ROWS", "3")   # by default slabs under five rows take the exchange-per-phase kernel
     rng = np.random.RandomState(7 * H + W)
     D = rng.standard_normal((H, W))
     D -= D.mean()
@@ -286,7 +287,7 @@ def test_resident_deep_halo_kernel_bit_exact(pcd, port, shape, monkeypatch):
     for n in (1, 2, 3, 10, 41):
         s.upload(D, phi0)
         info = s.run(n, 0.0)
-        assert s.resident_exchange == 2 and info["launches"] == 1
+        assert s.resident_exchange == 2 and info["launches"] == (1 if W <= 1024 else 4)   # + three transposes
         want, k, conv, last = port.poisson_rb(D, phi0, n, 0.0)
         got = s.download()
         assert np.array_equal(got, want), (shape, n, np.abs(got - want).max())
@@ -304,10 +305,12 @@ def test_resident_deep_halo_kernel_bit_exact(pcd, port, shape, monkeypatch):
     monkeypatch.setenv("PCD_RES_NO_DEEP", "1")
     s.upload(D2, z)
     classic = s.run(100000, 1e-6)
-    # strips of 8-9 rows (H > 1036) exist only in the deep-halo kernel: without it the solve runs on the wavefront path
-    assert s.resident_exchange == (1 if H <= 1036 else 0)
+    # strips of 8-9 rows (H > 1036) and transposed solves (W > 1024) exist only in the deep-halo kernel: without it the
+    # solve runs on the wavefront path
+    phase_fits = H <= 1036 and W <= 1024
+    assert s.resident_exchange == (1 if phase_fits else 0)
     assert classic["converged_at"] == deep["converged_at"]
-    if H <= 1036:
+    if phase_fits:
         assert classic["sweeps"] == deep["sweeps"]
         assert np.array_equal(s.download(), f_deep)
         assert classic["last_max_update"] == deep["last_max_update"]
