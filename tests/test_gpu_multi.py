@@ -90,13 +90,13 @@ def test_multi_gpu_stopping_rule_nan_and_thin_slabs(pcd, port, golden):
 def test_design_on_several_slabs_matches_one_gpu(pcd):
     """pcd_multi_attach: the context's transport and height iterations with their Poisson solves on row slabs."""
     from poisson_caustic_design_b200 import synth
-    res_w, aspect = 320, 4.0      # domain 1280 x 320: wavefront path on one GPU, same sweep schedule on slabs
+    res_w, aspect = 320, 4.0      # domain 1280 x 320, wavefront path on one GPU (forced: it would run on chip, transposed): same sweep schedule on slabs
     W = 4 * res_w
     H = int(W / aspect)
     image = synth.synth_density(W, H, 7)
 
     def run(devices):
-        cd = pcd.from_setup(synth.Setup(res_w, W, H), 0)
+        cd = pcd.from_setup(synth.Setup(res_w, W, H), 0, solver_path=pcd.SOLVER_TILED)
         cd.initialize_solvers(image)
         m = None
         if devices:
@@ -131,7 +131,9 @@ def test_cli_gpus_flag(pcd, golden, tmp_path):
     for gpus in (1, 2):
         out_dir = str(tmp_path / f"g{gpus}") + "/"
         os.makedirs(out_dir)
-        cmd = [CLI, f"--input_png={tmp_path}/hello.png", "--res_w=320", "--mesh_width=0.5", f"--output={out_dir}", f"--gpus={gpus}"]
+        # one GPU on the wavefront path (the slabs' sweep schedule; 1280 x 640 would otherwise run on chip, transposed)
+        cmd = [CLI, f"--input_png={tmp_path}/hello.png", "--res_w=320", "--mesh_width=0.5", f"--output={out_dir}", f"--gpus={gpus}",
+               "--solver_path=tiled"]
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(([float(m) for m in re.findall(r"Transport step size = ([0-9.]+)", r.stdout)],

@@ -170,7 +170,8 @@ def _design(pcd, res_w, aspect, seed, device=0):
     W = 4 * res_w
     H = int(W / aspect)
     image = synth.synth_density(W, H, seed)
-    cd = pcd.from_setup(synth.Setup(res_w, W, H), device)
+    # the wavefront path on purpose (its sweep schedule is the slab driver's): 1280 x 320 would otherwise run on chip, transposed
+    cd = pcd.from_setup(synth.Setup(res_w, W, H), device, solver_path=pcd.SOLVER_TILED)
     cd.initialize_solvers(image)
     return cd
 
@@ -179,7 +180,7 @@ def test_solve_hook_on_one_gpu_matches_the_builtin_solver(pcd):
     """The slab driver installed as the context's Poisson solver (pcd_set_solve_hook), world size 1: same sweep
     schedule as the built-in large-grid solver, so steps and fields are bit-identical."""
     from poisson_caustic_design_b200 import slab
-    ref = _design(pcd, 320, 4.0, 7)          # domain 1280 x 320: too wide for the resident kernel -> wavefront path
+    ref = _design(pcd, 320, 4.0, 7)          # domain 1280 x 320 on the wavefront path
     steps_ref = [ref.perform_transport_iteration() for _ in range(2)]
     info_ref = ref.last_solve_info()
     ref.perform_height_map_iteration(0)
