@@ -474,6 +474,9 @@ constexpr int RES_ERR_UNSUPPORTED = 2;
 #ifndef PCD_DEEP_PRESEND
 #define PCD_DEEP_PRESEND 1
 #endif
+#ifndef PCD_DEEP_SPLITBAR
+#define PCD_DEEP_SPLITBAR 0     // sweep-end warp-pair barrier as mbarrier arrive (after the last stores) / wait (before the next reads)
+#endif
 #ifndef PCD_DEEP_POLL_AFTER
 #define PCD_DEEP_POLL_AFTER 0   // interior rows of colour 0 updated before the first poll of a sweep is issued
 #endif
@@ -481,6 +484,22 @@ constexpr bool DEEP_DSMEM = PCD_DEEP_DSMEM != 0, DEEP_FASTPOLL = PCD_DEEP_FASTPO
 
 __device__ __forceinline__ double ll_value(const uint4 r) {
     return __longlong_as_double((long long)(((unsigned long long)r.z << 32) | r.x));
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra MBAR_WAIT_%=;\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
 template <int A, int B, class F>
@@ -571,6 +590,7 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
     static_assert(NR >= 2, "deep halos need two rows per slab");
     extern __shared__ double smem[];  // phi [nr_big][2][Kp] as in res_body, D likewise (DEEP_DSMEM), then the slots of the links inside a cluster
     __shared__ unsigned arrive[16];
+    __shared__ unsigned long long pairbar[16];   // DEEP_SPLITBAR: one mbarrier per pair of neighbouring warps (w, w+1), two arrivals each
     __shared__ int s_stop;
 
     const int tid = threadIdx.x, cta = blockIdx.x, k = tid, lane = tid & 31;
@@ -586,6 +606,7 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
     if (p.pair)
         for (int i = tid; i < 2 * RES2_SLOTS; i += RES_NT) pslot[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid < 16) arrive[tid] = 0u;
+    if (PCD_DEEP_SPLITBAR && tid < 16) mbar_init(&pairbar[tid], 2u);
     if (tid == 0) s_stop = 0;
     __syncthreads();
 
@@ -703,6 +724,12 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
                 if (!first) {
                     if (has_up) { ru1 = ll_issue(in_top + bin); ru2 = ll_issue(in_top + bin + RES_NT); if (edge_u) rue = ll_issue(in_top + bin + (keu - k)); }
                     if (has_dn) { rd1 = ll_issue(in_bot + bin); rd2 = ll_issue(in_bot + bin + RES_NT); if (edge_d) rde = ll_issue(in_bot + bin + (ked - k)); }
+                }
+                if (PCD_DEEP_SPLITBAR && sweep > 0) {   // the neighbouring warps' colour-1 values of the previous sweep
+                    const int wp = tid >> 5;
+                    const unsigned par = (unsigned)(sweep - 1) & 1u;
+                    if (wp > 0) mbar_wait(&pairbar[wp - 1], par);
+                    if (wp < RES_NT / 32 - 1) mbar_wait(&pairbar[wp], par);
                 }
                 deep_rows<NR, P0, EDGE, TR, 0, SPLIT, NR - 1>(s, smk, smD, 0.0, 0.0, lmax);
                 if (first) {   // (!DEEP_PRESEND) the halo rows of the first sweep come from the input field
@@ -830,7 +857,14 @@ __device__ __forceinline__ void deep_body(const ResParams &p, const int r0) {
             if ((conv_at == e + 1 && e >= 0) || (errv && *((volatile int *)&s_stop) == 0))
                 *((volatile int *)&s_stop) = sweep + 1 + RES_STOP_AHEAD;
         }
-        {
+        if (PCD_DEEP_SPLITBAR) {   // arrive now (this warp's stores of the sweep are done), wait before the next sweep's first reads
+            const int wp = tid >> 5;
+            __syncwarp();
+            if ((tid & 31) == 0) {
+                if (wp > 0) mbar_arrive(&pairbar[wp - 1]);
+                if (wp < RES_NT / 32 - 1) mbar_arrive(&pairbar[wp]);
+            }
+        } else {
             const int wp = tid >> 5;
             asm volatile("bar.sync %0, 64;" ::"r"(1 + (wp & ~1)) : "memory");
             if (wp >= 1 && wp <= RES_NT / 32 - 2) asm volatile("bar.sync %0, 64;" ::"r"((wp & 1) ? 1 + wp : wp) : "memory");

@@ -9,7 +9,9 @@ mkdir -p variants/obj
 for f in csrc/*.cu; do
   b=$(basename $f .cu)
   [ $b = sor_resident ] && continue
-  if [ ! -f variants/obj/$b.o ] || [ $f -nt variants/obj/$b.o ]; then nvcc $FLAGS -c $f -o variants/obj/$b.o & fi
+  stale=0
+  for d in $f csrc/*.h csrc/*.cuh ../include/pcd.h; do [ $d -nt variants/obj/$b.o ] && stale=1; done
+  if [ ! -f variants/obj/$b.o ] || [ $stale = 1 ]; then nvcc $FLAGS -c $f -o variants/obj/$b.o & fi
 done
 wait
 for spec in "$@"; do
