@@ -11,12 +11,13 @@
 // Three kernel families behind one entry point (solver_run), all producing the same bits:
 //   * streaming (this file): one launch per colour, phi/D streamed through L2/HBM; any grid size; with per-cell
 //                 neighbour masks it is also the path for D with NaN holes.
-//   * resident  (sor_resident.cu): ONE persistent kernel per solve for grids up to ~1024^2.  Each CTA (one per SM,
-//                 launched as clusters of two) owns a slab of rows; phi AND D of a thread's column pair live in
-//                 registers for the whole solve, only the left/right neighbour goes through shared memory; slab boundary
-//                 rows travel as 16-byte flag-in-data messages through L2 (DSMEM inside a pair), polled by the consuming
-//                 thread; no grid-wide and no CTA-wide barrier in the sweep loop; per-sweep verdicts are published with one
-//                 atomic per CTA and acted on with a fixed lag.
+//   * resident  (sor_resident.cu): ONE persistent kernel per solve for grids that fit on chip (one side <= 1024, the
+//                 other <= 1332; wide grids run transposed).  Each CTA (one per SM, launched as clusters of two) owns a slab
+//                 of rows; phi of a thread's column pair lives in registers for the whole solve (D in registers or shared
+//                 memory), only the left/right neighbour goes through shared memory; slab boundary rows travel as 16-byte
+//                 flag-in-data messages through L2 (DSMEM inside a pair), once per sweep (deep halos) or once per colour
+//                 phase, polled by the consuming thread; no grid-wide and no CTA-wide barrier in the sweep loop; per-sweep
+//                 verdicts are published with one atomic per CTA and acted on with a fixed lag.
 //   * wavefront (sor_tiled.cu): temporal blocking for larger grids and multi-GPU slabs, one persistent launch per block of
 //                 sweeps between two convergence tests.
 // plus the opt-in direct backend (dct_solver.cu).

@@ -25,6 +25,12 @@
 // omega/cnt factors are per-thread registers selected at compile time by (row class, column parity).
 // Threads whose strip touches NaN holes or phantom cells (odd W) run a per-cell masked path.
 //
+// Two kernels share this layout.  `sor_resident_kernel` (first half of the file) exchanges halos once per COLOUR PHASE and
+// handles everything: odd widths, NaN holes, slabs of one or two rows.  `sor_resident_deep_kernel` (second half; the one
+// that normally runs) exchanges once per SWEEP by updating the colour-0 cells of the rows just outside its slab
+// redundantly, keeps D in shared memory (up to 9 rows per CTA), and also solves grids wider than 1024 columns on the
+// transposed grid; it needs an even width and no NaN holes.  resident_plan / run_resident at the end choose between them.
+//
 // Update formula, ordering and stopping rule: src/solver.cpp:12-61,70-147 (see sor_kernels.cu header).
 #include <cooperative_groups.h>
 
