@@ -175,6 +175,13 @@ int pcd_solver_path_used(const pcd_solver *s);
 /* Which resident kernel the last pcd_solver_run used: 0 = none (another path), 1 = one neighbour exchange per colour
  * phase, 2 = one per sweep (deep halos: even width, no NaN holes, more than two rows per CTA).  Same results. */
 int pcd_solver_resident_exchange(const pcd_solver *s);
+/* What PCD_SOLVER_AUTO would choose for a width x height grid on a device with sm_count SMs -- pure host logic, no CUDA
+ * call (testable without a GPU).  *path: PCD_SOLVER_RESIDENT or PCD_SOLVER_TILED; for the resident path also the rows per
+ * CTA (3..9; 1..7 for the exchange-per-phase kernel), the number of CTAs, whether the solve runs on the transposed grid
+ * (more than 1024 columns) and whether only the deep-halo kernel applies (8-9 rows per CTA or transposed: NaN holes then
+ * go to the large-grid paths).  Any output pointer may be NULL. */
+int pcd_solver_plan(int width, int height, int sm_count, int *path, int *rows_per_cta, int *ctas, int *transposed,
+                    int *deep_only);
 
 /* ---- row-slab solver for multi-GPU runs (no counterpart in the reference) -------------------
  * One process per GPU owns global rows [row0, row0+rows) of a width x height grid plus GH =

@@ -95,6 +95,7 @@ ABI = [
     ("pcd_solver_path_used", C.c_int, [C.c_void_p]),
     ("pcd_solver_resident_exchange", C.c_int, [C.c_void_p]),
     ("pcd_resident_exchange", C.c_int, [C.c_void_p]),
+    ("pcd_solver_plan", C.c_int, [C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 5),
     ("pcd_slab_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     ("pcd_slab_destroy", None, [C.c_void_p]),
     ("pcd_slab_device_ptrs", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
@@ -234,6 +235,14 @@ class Solver:
     def resident_exchange(self) -> int:
         """Resident kernel of the last run: 0 none, 1 one exchange per colour phase, 2 one per sweep (deep halos)."""
         return lib().pcd_solver_resident_exchange(self._h)
+
+
+def solver_plan(width: int, height: int, sm_count: int = 148) -> dict:
+    """What SOLVER_AUTO chooses for a width x height grid on a device with ``sm_count`` SMs (host logic only, no GPU)."""
+    v = [C.c_int(0) for _ in range(5)]
+    _check(lib().pcd_solver_plan(int(width), int(height), int(sm_count), *[C.byref(x) for x in v]))
+    return {"path": SOLVER_PATH_NAMES.get(v[0].value, "?"), "rows_per_cta": v[1].value, "ctas": v[2].value,
+            "transposed": bool(v[3].value), "deep_only": bool(v[4].value)}
 
 
 class MultiGpuSolver:

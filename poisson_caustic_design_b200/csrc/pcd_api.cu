@@ -428,6 +428,20 @@ int pcd_solver_path_used(const pcd_solver *s) { return s ? s->path_used : -1; }
 
 int pcd_solver_resident_exchange(const pcd_solver *s) { return s ? s->res_exchange : -1; }
 
+int pcd_solver_plan(int width, int height, int sm_count, int *path, int *rows_per_cta, int *ctas, int *transposed,
+                    int *deep_only) {
+    if (width < 1 || height < 1 || height > 65535 || sm_count < 1) { set_error("pcd_solver_plan: invalid argument"); return PCD_ERR_INVALID; }
+    pcd_solver s;
+    s.W = width; s.H = height; s.sm_count = sm_count;
+    const int fits = pcd::resident_plan(&s);
+    if (path) *path = fits ? PCD_SOLVER_RESIDENT : PCD_SOLVER_TILED;
+    if (rows_per_cta) *rows_per_cta = fits ? s.res_rows_per_cta : 0;
+    if (ctas) *ctas = fits ? s.res_ctas : 0;
+    if (transposed) *transposed = fits && s.res_tr ? 1 : 0;
+    if (deep_only) *deep_only = fits && (s.res_tr || s.res_rows_per_cta > 7) ? 1 : 0;
+    return PCD_OK;
+}
+
 int pcd_poisson_solver(const double *D, double *phi, int width, int height, int max_iterations,
                        double convergence_threshold, int device, pcd_solve_info *info) {
     if (!D || !phi) { set_error("null field"); return PCD_ERR_INVALID; }

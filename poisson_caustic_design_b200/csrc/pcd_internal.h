@@ -96,6 +96,7 @@ namespace pcd {
 // run_resident's way of saying "not on chip after all" (never leaves solver_run): strips of 8-9 rows exist only in the
 // deep-halo kernel, which does not take NaN holes
 constexpr int PCD_RES_FALLBACK = 1000;
+int resident_plan(pcd_solver *s);   // 1 when the grid fits the on-chip path (fills s->res_*); host logic only (sor_resident.cu)
 int solver_init(pcd_solver *s, int W, int H, int device, int path, cudaStream_t stream);
 void solver_free(pcd_solver *s);
 // D_dev / phi_dev: device arrays of W*H doubles; phi in/out
