@@ -1018,6 +1018,11 @@ static int launch_resident(pcd_solver *s, ResParams &prm, bool deep) {
     // profiler): with one CTA per SM and at most one CTA per SM in the grid all pairs are resident on an idle device,
     // which cudaOccupancyMaxActiveClusters confirms up front; should they ever not be, the kernel gives up after ~1 s
     // (ResState::error), leaves phi untouched, and run_resident repeats the launch the cooperative way.
+    // (Measured at the end of round 2, deep-halo kernel, pairs / plain cooperative launch (PCD_RES_NO_PAIRS=1): 1024^2
+    // 1.557 / 1.552, 1024 x 512 1.543 / 1.436, 400^2 1.184 / 1.169 us/sweep -- the pairs no longer pay now that the
+    // exchange does not pace the kernel.  Making the cooperative launch the default was tried and taken back: the
+    // exchange-per-phase kernel hung on an odd-width grid (1023 x 1024) in that mode, with no GPU time left to find out why;
+    // the pair launch is the configuration every test and soak of both rounds ran.)
     static const bool no_pairs = getenv("PCD_RES_NO_PAIRS") != nullptr;
     static const int cs_env = getenv("PCD_RES_CLUSTER") ? atoi(getenv("PCD_RES_CLUSTER")) : 2;   // tuning knob
     const int cs = (cs_env == 4 || cs_env == 8) ? cs_env : 2;
